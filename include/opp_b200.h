@@ -1,0 +1,173 @@
+/*
+ * opp_b200.h -- C-ABI of the B200-native openpose-plus post-processing path
+ * (part-confidence maps + part-affinity fields in, grouped COCO-18 skeletons out).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  Two host sides sit
+ * on top of it: the C++ `paf_processor` subclass behind the unchanged `create_paf_processor`
+ * (csrc/paf_processor.cpp; replaces /root/reference src/paf.cpp:19-57,340-346) and the Python
+ * `PostProcessor` (openpose_plus_b200/post_process.py; replaces
+ * openpose_plus/inference/post_process.py:109-150) through ctypes.
+ *
+ * Everything behind it runs as hand-written sm_100a CUDA kernels; there is no CPU fallback.
+ * Reference file:line citations are relative to /root/reference.
+ */
+#ifndef OPP_B200_H
+#define OPP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPP_N_PARTS 18 /* COCO_N_PARTS, include/openpose-plus/coco.h:5 */
+#define OPP_N_PAIRS 19 /* COCO_N_PAIRS, include/openpose-plus/coco.h:6 */
+#define OPP_N_HEAT 19  /* n_joins,  include/openpose-plus.h:11 */
+#define OPP_N_PAF 38   /* 2 * n_connections, include/openpose-plus.h:12 */
+
+/* status codes (the reference has none: cuDNN errors exit(1), src/cudnn_traits.hpp:11-20) */
+enum {
+    OPP_OK = 0,
+    OPP_ERR_INVALID = 1,  /* bad argument / unsupported geometry */
+    OPP_ERR_CUDA = 2,     /* a CUDA runtime call failed; see opp_last_error */
+    OPP_ERR_NO_DEVICE = 3,
+    OPP_ERR_BUSY = 4      /* no free pipeline slot (opp_submit without opp_wait) */
+};
+
+/* per-frame flag bits written to frame_flags[] */
+enum {
+    OPP_FLAG_PEAK_OVERFLOW = 1,   /* a part had more peaks than max_peaks_per_part: result invalid */
+    OPP_FLAG_CAND_OVERFLOW = 2,   /* a limb had more accepted candidates than max_cands_per_limb */
+    OPP_FLAG_HUMAN_OVERFLOW = 4,  /* more partial humans than max_humans */
+    OPP_FLAG_UB_STALE_INDEX = 8,  /* reference would index human_refs[] beyond its historical size (src/paf.cpp:204,211-212) */
+    OPP_FLAG_UB_PEAK_INDEX = 16,  /* reference would index all_peaks[] with a corrupted merged id (src/paf.cpp:224,301) */
+    OPP_FLAG_UB_ERASE_PAST_END = 32 /* reference erases at a stale id >= size() (src/paf.cpp:231); restated as libstdc++ 13 behaves */
+};
+
+enum { OPP_MEM_HOST = 0, OPP_MEM_DEVICE = 1 };
+enum { OPP_LAYOUT_CHW = 0, OPP_LAYOUT_HWC = 1 };
+
+/* include/openpose-plus/human.h:8-15 (bool + 3 pad bytes, then 3 floats) */
+typedef struct {
+    uint8_t has_value;
+    uint8_t pad_[3];
+    float x, y, score;
+} opp_body_part_t;
+
+/* include/openpose-plus/human.h:17-34 -- human_t, 292 bytes; x,y are pixels of the up-sampled map */
+typedef struct {
+    opp_body_part_t parts[OPP_N_PARTS];
+    float score;
+} opp_human_t;
+
+/* src/post-process.h:132-137 -- peak_info */
+typedef struct {
+    int32_t part_id;
+    int32_t x, y;
+    float score;
+    int32_t id;
+} opp_peak_t;
+
+/* include/openpose-plus/human.h:49-55 -- Connection (cidN == peak_idN, src/paf.cpp:166-170) */
+typedef struct {
+    int32_t cid1, cid2;
+    float score;
+} opp_conn_t;
+
+/* Arguments of create_paf_processor (include/openpose-plus.hpp:54-64) plus capacities.  The
+ * reference grows std::vectors without bound; fixed capacities are reported through frame_flags. */
+typedef struct {
+    int32_t feat_h, feat_w;      /* "input_height/input_width": size of the feature maps */
+    int32_t out_h, out_w;        /* "height/width": size the maps are up-sampled to */
+    int32_t n_joins;             /* must be 19 */
+    int32_t n_connections;       /* must be 19 */
+    int32_t gauss_kernel_size;   /* odd, 1..63 */
+    int32_t max_batch;           /* frames per opp_process/opp_submit call */
+    int32_t device;              /* CUDA ordinal, -1 = current device */
+    int32_t max_peaks_per_part;  /* default 128 */
+    int32_t max_cands_per_limb;  /* default 1024 */
+    int32_t max_humans;          /* default 128 (counts partial humans during assembly) */
+    int32_t n_slots;             /* batches in flight (own stream + buffers each), default 3 */
+    int32_t reserved[3];
+} opp_config_t;
+
+/* One batch of frames. */
+typedef struct {
+    const float *conf;     /* [n, 19, h, w] (CHW) or [n, h, w, 19] (HWC) */
+    const float *paf;      /* [n, 38, h, w] (CHW) or [n, h, w, 38] (HWC) */
+    int32_t n_frames;      /* 1..max_batch */
+    int32_t in_mem;        /* OPP_MEM_HOST | OPP_MEM_DEVICE */
+    int32_t in_layout;     /* OPP_LAYOUT_CHW | OPP_LAYOUT_HWC */
+    int32_t out_mem;       /* where humans / n_humans / frame_flags live */
+    opp_human_t *humans;   /* [n, max_humans]; frame f's humans are humans[f*max_humans .. +n_humans[f]) */
+    int32_t *n_humans;     /* [n] */
+    int32_t *frame_flags;  /* [n] OPP_FLAG_* bits, may be NULL */
+    /* Optional materialised up-sampled maps (DEVICE pointers), what the reference keeps in
+     * upsample_conf/upsample_paf (src/paf.cpp:74-75) and the Python entry returns
+     * (post_process.py:150).  NULL = not written (the skeletons are identical either way). */
+    float *conf_up;        /* [n, 19, H, W] (CHW) or [n, H, W, 19] (up_layout HWC) */
+    float *paf_up;         /* [n, 38, H, W] (CHW) or [n, H, W, 38] */
+    int32_t up_layout;
+    int32_t reserved[3];
+} opp_batch_t;
+
+typedef struct opp_handle_s *opp_handle_t;
+
+void opp_config_default(opp_config_t *cfg, int feat_h, int feat_w, int out_h, int out_w, int gauss_kernel_size);
+
+/* replaces paf_processor_impl's constructor (src/paf.cpp:22-36) and peak_finder_t's (src/post-process.h:142-153) */
+int opp_create(const opp_config_t *cfg, opp_handle_t *out);
+void opp_destroy(opp_handle_t h);
+
+/* replaces paf_processor_impl::operator() (src/paf.cpp:38-57) for n frames; returns when outputs are written */
+int opp_process(opp_handle_t h, const opp_batch_t *batch);
+
+/* Pipelined form: opp_submit enqueues a batch on the next free slot and returns a ticket;
+ * opp_wait blocks until that batch's outputs are written.  Up to n_slots batches in flight. */
+int opp_submit(opp_handle_t h, const opp_batch_t *batch, int *ticket);
+int opp_wait(opp_handle_t h, int ticket);
+
+/* Device time (ms, CUDA events on the slot's stream) of the last completed batch on a ticket's slot. */
+float opp_last_batch_ms(opp_handle_t h, int ticket);
+/* Number of kernel launches issued by this handle so far. */
+int64_t opp_launch_count(opp_handle_t h);
+
+/* Pinned host memory for opp_batch_t host buffers (pageable memory also works, slower). */
+void *opp_host_alloc(size_t bytes);
+void opp_host_free(void *p);
+
+/* Intermediates of the last batch processed on `ticket`'s slot, for parity tests.  Each call copies
+ * up to cap elements of frame `frame` to host memory and returns the element count (<0 on error).
+ *   OPP_DBG_PEAKS  -> opp_peak_t[]  (all_peaks in raster order, src/post-process.h:190-198)
+ *   OPP_DBG_CONNS  -> opp_conn_t[]  of limb `index` in acceptance order (src/paf.cpp:154-173)
+ *   OPP_DBG_PARTS  -> int32[18] part -> peak id of surviving human `index` (human_ref_t::parts) */
+enum { OPP_DBG_PEAKS = 0, OPP_DBG_CONNS = 1, OPP_DBG_PARTS = 2, OPP_DBG_COUNTS = 3 };
+int opp_debug_fetch(opp_handle_t h, int ticket, int what, int frame, int index, void *dst, int cap);
+
+/* Stand-alone stages on device memory (used by tests and the bench to time kernels in isolation).
+ * stream is a cudaStream_t (NULL = the handle's slot-0 stream). */
+int opp_resize_device(opp_handle_t h, const float *src, int channels, int n_frames, float *dst, int dst_layout, void *stream);
+
+/* Peak finding alone (smooth + NMS + raster-order peak list) on device feature maps, on the caller's
+ * stream, writing the slot-0 scratch buffers: lets the bench time the kernel with its own events. */
+int opp_peaks_device(opp_handle_t h, const float *conf, int n_frames, void *stream);
+
+/* Device-side stopwatch over ALL slot streams: opp_timer_start records an event after everything
+ * already enqueued; opp_timer_stop joins every slot stream, records, waits, and returns the elapsed
+ * milliseconds between the two events (CUDA events, not wall clock). */
+int opp_timer_start(opp_handle_t h);
+float opp_timer_stop(opp_handle_t h);
+
+const char *opp_last_error(opp_handle_t h);
+const char *opp_version(void);
+
+/* The reference declares this and never defines it (include/openpose-plus.h:18-22).  Defined here on
+ * top of the path above: runs one frame (feature maps of size height x width, up-sampled x8 like
+ * every caller in the reference, gauss kernel 17) and prints each human like human_t::print. */
+void process_conf_paf(int height, int width, int n_joins, int n_connections, const float *peaks_, const float *pafmap_);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,40 @@
+"""Builds the in-tree CUDA library (sm_100a only) with nvcc; no torch involved.
+
+    python -m openpose_plus_b200.build [--force]
+
+Output: openpose_plus_b200/libopp_b200.so (git-ignored; it travels to the GPU box with the snapshot).
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libopp_b200.so")
+SOURCES = ["opp_kernels.cu", "opp_capi.cu", "paf_processor.cpp"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+# -fmad=false: every float operation that decides an output must round exactly like the
+# reference's strict-IEEE scalar code; nothing on this path wants a fused multiply-add.
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-shared", "-I", os.path.join(ROOT, "include")]
+
+
+def stale():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "opp_b200.h"), __file__]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return OUT
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
+    subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

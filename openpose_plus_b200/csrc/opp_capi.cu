@@ -1,0 +1,739 @@
+// Host runtime behind the C-ABI of include/opp_b200.h: per-GPU handle, pipeline slots (own stream,
+// device arena, pinned result buffers), and the stage sequencing that replaces
+// paf_processor_impl::operator() (/root/reference src/paf.cpp:38-57).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "opp_kernels.cuh"
+
+namespace
+{
+thread_local std::string g_err;
+
+void set_err(std::string *dst, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    if (dst) *dst = buf;
+}
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr; // materialising resize runs beside peak finding / grouping
+    cudaEvent_t ev_start = nullptr, ev_done = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    // device arena
+    float *d_conf = nullptr, *d_paf = nullptr; // staged feature maps [B,19,h,w] / [B,38,h,w]
+    float *d_hwc = nullptr;                    // staging for channels-last input
+    float *d_conf_up = nullptr;                // only for the generic peak kernel
+    int *d_counters = nullptr;                 // pk_cnt[B*18] | k2_done[B] | k3_done[B] | stats[B*4] | flags[B]
+    int *d_pk_key = nullptr;
+    opp_peak_t *d_peaks = nullptr;
+    int *d_part_ofs = nullptr;
+    opp_conn_t *d_conns = nullptr;
+    int *d_n_conns = nullptr;
+    float *d_cand = nullptr;
+    opp_human_t *d_humans = nullptr;
+    int *d_n_humans = nullptr;
+    int *d_href_parts = nullptr;
+    // pinned results
+    opp_human_t *h_humans = nullptr;
+    int *h_n_humans = nullptr, *h_flags = nullptr;
+    // in-flight batch
+    bool busy = false;
+    int n_frames = 0;
+    opp_batch_t batch{};
+    float last_ms = 0.f;
+    int ticket = -1;
+};
+
+} // namespace
+
+struct opp_handle_s {
+    opp_config_t cfg{};
+    OppGeom g{};
+    int device = 0;
+    int max_smem = 0, sm_count = 0;
+    bool fast_k2 = false;
+    float taps[OPP_MAX_KSIZE + 1]{};
+    int *d_xofs = nullptr, *d_yofs = nullptr;
+    float *d_alpha = nullptr, *d_beta = nullptr;
+    std::vector<Slot> slots;
+    int next_slot = 0;
+    int next_ticket = 0;
+    int64_t launches = 0;
+    std::string err;
+    size_t counters_ints = 0;
+    // K3 shared-memory plan
+    K3Params k3_plan{};
+    size_t k3_smem = 0;
+    int force_tw = 0, force_th = 0;
+    cudaStream_t timer_stream = nullptr;
+    cudaEvent_t timer_t0 = nullptr, timer_t1 = nullptr;
+};
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            set_err(&h->err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return OPP_ERR_CUDA;                                                                      \
+        }                                                                                             \
+    } while (0)
+
+namespace
+{
+// cv::getGaussianKernel(k, sigma, CV_32F): taps in double, normalised, rounded to float.
+void gauss_taps(int k, double sigma, float *taps)
+{
+    double t[OPP_MAX_KSIZE + 1], sum = 0;
+    const double scale2x = -0.5 / (sigma * sigma);
+    for (int i = 0; i < k; ++i) {
+        const double x = i - (k - 1) * 0.5;
+        t[i] = std::exp(scale2x * x * x);
+        sum += t[i];
+    }
+    const double inv = 1.0 / sum;
+    for (int i = 0; i < k; ++i) taps[i] = (float)(t[i] * inv);
+}
+
+// Area-mode coefficients of cv::resize(INTER_AREA) when up-sampling: s = floor(d*scale),
+// f = (float)((d+1) - (s+1)*inv_scale), f = f <= 0 ? 0 : f - floor(f); x additionally clamps at the
+// right edge.  Same statement as oracle/opp_oracle.c (validated against cv2 there).
+int area_coeffs(int ssize, int dsize, bool clamp_edge, std::vector<int> &ofs, std::vector<float> &co)
+{
+    const double inv_scale = (double)dsize / ssize, scale = 1. / inv_scale;
+    int dmax = dsize;
+    ofs.resize(dsize), co.resize(2 * (size_t)dsize);
+    for (int d = 0; d < dsize; ++d) {
+        int s = (int)std::floor(d * scale);
+        float f = (float)((d + 1) - (s + 1) * inv_scale);
+        f = f <= 0 ? 0.f : f - (float)(int)std::floor(f);
+        if (clamp_edge && s + 1 >= ssize) {
+            if (d < dmax) dmax = d;
+            if (s >= ssize - 1) f = 0, s = ssize - 1;
+        }
+        ofs[d] = s, co[2 * d] = 1.f - f, co[2 * d + 1] = f;
+    }
+    return dmax;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void plan_k3_smem(opp_handle_s *h)
+{
+    K3Params &p = h->k3_plan;
+    const OppGeom &g = h->g;
+    const int capP = h->cfg.max_peaks_per_part, capC = h->cfg.max_cands_per_limb, capH = h->cfg.max_humans;
+    const size_t budget = (size_t)h->max_smem;
+    // scoring / matching phase
+    size_t off = 0;
+    const size_t paf_bytes = 2 * (size_t)g.h * g.w * sizeof(float);
+    const size_t fixed = 2 * (size_t)capP * sizeof(int2) + align_up(2 * (size_t)capP, 16) + 64;
+    const size_t cand_bytes = 2 * (size_t)capC * 12;
+    p.cand_in_smem = (fixed + cand_bytes) <= budget / 2;
+    p.paf_in_smem = (fixed + (p.cand_in_smem ? cand_bytes : 0) + paf_bytes) <= (size_t)(budget * 0.45);
+    p.off_paf = (int)off;
+    if (p.paf_in_smem) off += align_up(paf_bytes, 16);
+    p.off_pk = (int)off, off += 2 * (size_t)capP * sizeof(int2);
+    p.off_cand = (int)off;
+    if (p.cand_in_smem) off += align_up(cand_bytes, 16);
+    p.off_used = (int)off, off += align_up(2 * (size_t)capP, 16);
+    p.off_misc = (int)off, off += 64;
+    const size_t phase1 = off;
+    // assembly phase (re-uses the same bytes)
+    off = 0;
+    p.off_href = 0, off += align_up((size_t)capH * 21 * sizeof(int), 16);
+    p.off_conn = (int)off, off += align_up((size_t)capP * sizeof(opp_conn_t), 16);
+    const size_t score_bytes = (size_t)OPP_N_PARTS * capP * sizeof(float);
+    p.score_in_smem = off + score_bytes <= budget / 2;
+    p.off_score = (int)off;
+    if (p.score_in_smem) off += score_bytes;
+    h->k3_smem = phase1 > off ? phase1 : off;
+}
+
+int free_slot(opp_handle_s *h, Slot &s)
+{
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    cudaFree(s.d_conf), cudaFree(s.d_paf), cudaFree(s.d_hwc), cudaFree(s.d_conf_up), cudaFree(s.d_counters);
+    cudaFree(s.d_pk_key), cudaFree(s.d_peaks), cudaFree(s.d_part_ofs), cudaFree(s.d_conns), cudaFree(s.d_n_conns);
+    cudaFree(s.d_cand), cudaFree(s.d_humans), cudaFree(s.d_n_humans), cudaFree(s.d_href_parts);
+    cudaFreeHost(s.h_humans), cudaFreeHost(s.h_n_humans), cudaFreeHost(s.h_flags);
+    if (s.ev_start) cudaEventDestroy(s.ev_start);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+    if (s.ev_join) cudaEventDestroy(s.ev_join);
+    if (s.side) cudaStreamDestroy(s.side);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = Slot();
+    (void)h;
+    return 0;
+}
+
+int alloc_slot(opp_handle_s *h, Slot &s)
+{
+    const opp_config_t &c = h->cfg;
+    const size_t B = c.max_batch, hw = (size_t)c.feat_h * c.feat_w;
+    const int capP = c.max_peaks_per_part, capC = c.max_cands_per_limb, capH = c.max_humans;
+    CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s.ev_start));
+    CU(cudaEventCreate(&s.ev_done));
+    CU(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
+    CU(cudaMalloc(&s.d_conf, B * OPP_N_HEAT * hw * sizeof(float)));
+    CU(cudaMalloc(&s.d_paf, B * OPP_N_PAF * hw * sizeof(float)));
+    CU(cudaMalloc(&s.d_counters, h->counters_ints * sizeof(int)));
+    CU(cudaMemset(s.d_counters, 0, h->counters_ints * sizeof(int)));
+    CU(cudaMalloc(&s.d_pk_key, B * OPP_N_PARTS * capP * sizeof(int)));
+    CU(cudaMalloc(&s.d_peaks, B * OPP_N_PARTS * capP * sizeof(opp_peak_t)));
+    CU(cudaMalloc(&s.d_part_ofs, B * (OPP_N_PARTS + 1) * sizeof(int)));
+    CU(cudaMalloc(&s.d_conns, B * OPP_N_PAIRS * capP * sizeof(opp_conn_t)));
+    CU(cudaMalloc(&s.d_n_conns, B * OPP_N_PAIRS * sizeof(int)));
+    if (!h->k3_plan.cand_in_smem) CU(cudaMalloc(&s.d_cand, B * OPP_N_PAIRS * 2 * (size_t)capC * 12));
+    CU(cudaMalloc(&s.d_humans, B * capH * sizeof(opp_human_t)));
+    CU(cudaMalloc(&s.d_n_humans, B * sizeof(int)));
+    CU(cudaMalloc(&s.d_href_parts, B * capH * OPP_N_PARTS * sizeof(int)));
+    CU(cudaMemset(s.d_n_conns, 0, B * OPP_N_PAIRS * sizeof(int)));
+    CU(cudaMemset(s.d_part_ofs, 0, B * (OPP_N_PARTS + 1) * sizeof(int)));
+    CU(cudaMemset(s.d_n_humans, 0, B * sizeof(int)));
+    CU(cudaMallocHost(&s.h_humans, B * capH * sizeof(opp_human_t)));
+    CU(cudaMallocHost(&s.h_n_humans, B * sizeof(int)));
+    CU(cudaMallocHost(&s.h_flags, B * sizeof(int)));
+    return OPP_OK;
+}
+
+int *cnt_pk(opp_handle_s *, Slot &s) { return s.d_counters; }
+int *cnt_k2(opp_handle_s *h, Slot &s) { return s.d_counters + (size_t)h->cfg.max_batch * OPP_N_PARTS; }
+int *cnt_k3(opp_handle_s *h, Slot &s) { return cnt_k2(h, s) + h->cfg.max_batch; }
+int *cnt_stats(opp_handle_s *h, Slot &s) { return cnt_k3(h, s) + h->cfg.max_batch; }
+int *cnt_flags(opp_handle_s *h, Slot &s) { return cnt_stats(h, s) + (size_t)h->cfg.max_batch * 4; }
+
+void choose_k2_tiles(opp_handle_s *h, int n_frames, int &tw, int &th)
+{
+    const OppGeom &g = h->g;
+    // column strips of about 240 output columns: 8 groups of 30 columns, one per warp
+    int nxs = (g.W + 239) / 240;
+    if (nxs < 1) nxs = 1;
+    tw = (g.w + nxs - 1) / nxs;
+    th = g.h;
+    // small batches: split rows too until the grid covers the chip about twice
+    const long want = 2L * h->sm_count;
+    while ((long)n_frames * OPP_N_PARTS * ((g.w + tw - 1) / tw) * ((g.h + th - 1) / th) < want && th > 6) th = (th + 1) / 2;
+    while (k2_fast_smem_bytes(g, tw, th) > (size_t)h->max_smem / 2 && th > 4) th = (th + 1) / 2;
+    if (h->force_tw > 0) tw = h->force_tw;
+    if (h->force_th > 0) th = h->force_th;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *opp_version(void) { return "openpose-plus-b200 0.1 (sm_100a)"; }
+
+const char *opp_last_error(opp_handle_t h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+void opp_config_default(opp_config_t *cfg, int feat_h, int feat_w, int out_h, int out_w, int gauss_kernel_size)
+{
+    std::memset(cfg, 0, sizeof *cfg);
+    cfg->feat_h = feat_h, cfg->feat_w = feat_w, cfg->out_h = out_h, cfg->out_w = out_w;
+    cfg->n_joins = OPP_N_HEAT, cfg->n_connections = OPP_N_PAIRS;
+    cfg->gauss_kernel_size = gauss_kernel_size;
+    cfg->max_batch = 64;
+    cfg->device = -1;
+    cfg->max_peaks_per_part = 128;
+    cfg->max_cands_per_limb = 1024;
+    cfg->max_humans = 128;
+    cfg->n_slots = 3;
+}
+
+void *opp_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        set_err(nullptr, "cudaMallocHost(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void opp_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+void opp_destroy(opp_handle_t h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto &s : h->slots) free_slot(h, s);
+    if (h->timer_t0) cudaEventDestroy(h->timer_t0);
+    if (h->timer_t1) cudaEventDestroy(h->timer_t1);
+    if (h->timer_stream) cudaStreamDestroy(h->timer_stream);
+    cudaFree(h->d_xofs), cudaFree(h->d_yofs), cudaFree(h->d_alpha), cudaFree(h->d_beta);
+    delete h;
+}
+
+int opp_create(const opp_config_t *cfg, opp_handle_t *out)
+{
+    if (!cfg || !out) {
+        set_err(nullptr, "opp_create: null argument");
+        return OPP_ERR_INVALID;
+    }
+    *out = nullptr;
+    opp_config_t c = *cfg;
+    if (c.max_batch <= 0) c.max_batch = 64;
+    if (c.max_peaks_per_part <= 0) c.max_peaks_per_part = 128;
+    if (c.max_cands_per_limb <= 0) c.max_cands_per_limb = 1024;
+    if (c.max_humans <= 0) c.max_humans = 128;
+    if (c.n_slots <= 0) c.n_slots = 3;
+    const int k = c.gauss_kernel_size;
+    if (c.n_joins != OPP_N_HEAT || c.n_connections != OPP_N_PAIRS) {
+        set_err(nullptr, "opp_create: n_joins and n_connections must be 19 (include/openpose-plus.hpp:63)");
+        return OPP_ERR_INVALID;
+    }
+    if (c.feat_h < 2 || c.feat_w < 2 || c.out_h < c.feat_h || c.out_w < c.feat_w) {
+        set_err(nullptr, "opp_create: output size must be >= feature size >= 2 (INTER_AREA up-sampling only)");
+        return OPP_ERR_INVALID;
+    }
+    if (k < 1 || (k & 1) == 0 || k > OPP_MAX_KSIZE || k / 2 >= c.out_h - 1 || k / 2 >= c.out_w - 1) {
+        set_err(nullptr, "opp_create: gauss_kernel_size must be odd, 1..%d and smaller than the image", OPP_MAX_KSIZE);
+        return OPP_ERR_INVALID;
+    }
+    if ((long)OPP_N_PARTS * c.max_peaks_per_part > 1 << 20 || c.max_humans > 8192) {
+        set_err(nullptr, "opp_create: capacities too large");
+        return OPP_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_err(nullptr, "opp_create: no CUDA device (this path has no CPU fallback)");
+        return OPP_ERR_NO_DEVICE;
+    }
+    opp_handle_s *h = new opp_handle_s();
+    h->cfg = c;
+    int rc = OPP_OK;
+    auto body = [&]() -> int {
+        if (c.device >= 0)
+            CU(cudaSetDevice(c.device));
+        CU(cudaGetDevice(&h->device));
+        h->cfg.device = h->device;
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, h->device));
+        if (prop.major < 10) {
+            set_err(&h->err, "opp_create: device %d is sm_%d%d; this library is built for sm_100a only", h->device, prop.major, prop.minor);
+            return OPP_ERR_NO_DEVICE;
+        }
+        h->max_smem = (int)prop.sharedMemPerBlockOptin;
+        h->sm_count = prop.multiProcessorCount;
+        CU(opp_kernels_init(h->max_smem));
+        OppGeom &g = h->g;
+        g.h = c.feat_h, g.w = c.feat_w, g.H = c.out_h, g.W = c.out_w, g.K = k, g.R = k / 2;
+        g.S = (c.out_h % c.feat_h == 0 && c.out_w % c.feat_w == 0 && c.out_h / c.feat_h == c.out_w / c.feat_w) ? c.out_h / c.feat_h : 0;
+        gauss_taps(k, 3.0, h->taps); // sigma fixed by the reference, src/post-process.h:54
+        std::vector<int> xo, yo;
+        std::vector<float> al, be;
+        g.xmax = area_coeffs(g.w, g.W, true, xo, al);
+        area_coeffs(g.h, g.H, false, yo, be);
+        CU(cudaMalloc(&h->d_xofs, xo.size() * sizeof(int)));
+        CU(cudaMalloc(&h->d_yofs, yo.size() * sizeof(int)));
+        CU(cudaMalloc(&h->d_alpha, al.size() * sizeof(float)));
+        CU(cudaMalloc(&h->d_beta, be.size() * sizeof(float)));
+        CU(cudaMemcpy(h->d_xofs, xo.data(), xo.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->d_yofs, yo.data(), yo.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->d_alpha, al.data(), al.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->d_beta, be.data(), be.size() * sizeof(float), cudaMemcpyHostToDevice));
+        g.xofs = h->d_xofs, g.yofs = h->d_yofs, g.alpha = h->d_alpha, g.beta = h->d_beta;
+        h->fast_k2 = k2_fast_supported(g);
+        if (const char *e = getenv("OPP_FORCE_GENERIC")) {
+            if (atoi(e)) h->fast_k2 = false;
+        }
+        if (const char *e = getenv("OPP_K2_TW")) h->force_tw = atoi(e);
+        if (const char *e = getenv("OPP_K2_TH")) h->force_th = atoi(e);
+        plan_k3_smem(h);
+        if (h->k3_smem > (size_t)h->max_smem) {
+            set_err(&h->err, "opp_create: capacities need %zu bytes of shared memory (> %d)", h->k3_smem, h->max_smem);
+            return OPP_ERR_INVALID;
+        }
+        h->counters_ints = (size_t)c.max_batch * (OPP_N_PARTS + 1 + 1 + 4 + 1);
+        CU(cudaStreamCreateWithFlags(&h->timer_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&h->timer_t0));
+        CU(cudaEventCreate(&h->timer_t1));
+        h->slots.resize(c.n_slots);
+        for (auto &s : h->slots) {
+            int r = alloc_slot(h, s);
+            if (r != OPP_OK) return r;
+        }
+        return OPP_OK;
+    };
+    rc = body();
+    if (rc != OPP_OK) {
+        g_err = h->err;
+        opp_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return OPP_OK;
+}
+
+static int fill_k2(opp_handle_s *h, Slot &s, const float *conf, const float *conf_up, int n, K2Params &k2);
+
+static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
+{
+    const opp_config_t &c = h->cfg;
+    const OppGeom &g = h->g;
+    const int n = b.n_frames;
+    const size_t hw = (size_t)g.h * g.w, HW = (size_t)g.H * g.W;
+    cudaStream_t st = s.stream;
+    CU(cudaEventRecord(s.ev_start, st));
+    CU(cudaMemsetAsync(s.d_counters, 0, h->counters_ints * sizeof(int), st));
+
+    // ---- inputs
+    const float *conf = nullptr, *paf = nullptr;
+    const cudaMemcpyKind in_kind = b.in_mem == OPP_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (b.in_layout == OPP_LAYOUT_HWC) {
+        if (!s.d_hwc) CU(cudaMalloc(&s.d_hwc, (size_t)c.max_batch * OPP_N_PAF * hw * sizeof(float)));
+        const float *src = b.conf;
+        if (b.in_mem == OPP_MEM_HOST) {
+            CU(cudaMemcpyAsync(s.d_hwc, b.conf, n * OPP_N_HEAT * hw * sizeof(float), in_kind, st));
+            src = s.d_hwc;
+        }
+        CU(launch_hwc_to_chw(src, s.d_conf, n, OPP_N_HEAT, g.h, g.w, st));
+        src = b.paf;
+        if (b.in_mem == OPP_MEM_HOST) {
+            CU(cudaMemcpyAsync(s.d_hwc, b.paf, n * OPP_N_PAF * hw * sizeof(float), in_kind, st));
+            src = s.d_hwc;
+        }
+        CU(launch_hwc_to_chw(src, s.d_paf, n, OPP_N_PAF, g.h, g.w, st));
+        h->launches += 2;
+        conf = s.d_conf, paf = s.d_paf;
+    } else if (b.in_mem == OPP_MEM_HOST) {
+        CU(cudaMemcpyAsync(s.d_conf, b.conf, n * OPP_N_HEAT * hw * sizeof(float), in_kind, st));
+        CU(cudaMemcpyAsync(s.d_paf, b.paf, n * OPP_N_PAF * hw * sizeof(float), in_kind, st));
+        conf = s.d_conf, paf = s.d_paf;
+    } else {
+        conf = b.conf, paf = b.paf; // device-resident feature maps are used in place
+    }
+
+    // ---- optional materialised up-sampled maps, beside the rest (they are outputs only)
+    const bool want_up = b.conf_up || b.paf_up;
+    const bool generic_needs_conf_up = !h->fast_k2;
+    bool forked = false;
+    auto resize_on = [&](cudaStream_t rs, const float *src, float *dst, int C, int layout) -> int {
+        K1Params k1{};
+        k1.g = g, k1.src = src, k1.dst = dst, k1.C = C, k1.n = n, k1.layout = layout;
+        CU(launch_k1(k1, rs));
+        h->launches += 1;
+        return OPP_OK;
+    };
+    const float *conf_up_for_k2 = nullptr;
+    if (generic_needs_conf_up) {
+        // the generic peak kernel reads the materialised heat map: CHW, on the main stream
+        if (b.conf_up && b.up_layout == OPP_LAYOUT_CHW) {
+            int r = resize_on(st, conf, b.conf_up, OPP_N_HEAT, OPP_LAYOUT_CHW);
+            if (r) return r;
+            conf_up_for_k2 = b.conf_up;
+        } else {
+            if (!s.d_conf_up) CU(cudaMalloc(&s.d_conf_up, (size_t)c.max_batch * OPP_N_HEAT * HW * sizeof(float)));
+            int r = resize_on(st, conf, s.d_conf_up, OPP_N_HEAT, OPP_LAYOUT_CHW);
+            if (r) return r;
+            conf_up_for_k2 = s.d_conf_up;
+        }
+    }
+    if (want_up) {
+        CU(cudaEventRecord(s.ev_fork, st));
+        CU(cudaStreamWaitEvent(s.side, s.ev_fork, 0));
+        forked = true;
+        if (b.conf_up && !(generic_needs_conf_up && b.up_layout == OPP_LAYOUT_CHW)) {
+            int r = resize_on(s.side, conf, b.conf_up, OPP_N_HEAT, b.up_layout);
+            if (r) return r;
+        }
+        if (b.paf_up) {
+            int r = resize_on(s.side, paf, b.paf_up, OPP_N_PAF, b.up_layout);
+            if (r) return r;
+        }
+    }
+
+    // ---- peaks
+    K2Params k2{};
+    fill_k2(h, s, conf, conf_up_for_k2, n, k2);
+    int *d_flags = cnt_flags(h, s);
+    if (h->fast_k2) {
+        CU(launch_k2_fast(k2, n, st));
+    } else {
+        CU(launch_k2_generic(k2, n, st));
+    }
+    h->launches += 1;
+
+    // ---- limbs, matching, assembly
+    K3Params k3 = h->k3_plan;
+    k3.g = g, k3.paf = paf, k3.peaks = s.d_peaks, k3.part_ofs = s.d_part_ofs;
+    k3.capP = c.max_peaks_per_part, k3.capC = c.max_cands_per_limb, k3.capH = c.max_humans;
+    k3.cnt = k2.cnt;
+    k3.cand_scratch = s.d_cand, k3.conns = s.d_conns, k3.n_conns = s.d_n_conns;
+    const bool dev_out = b.out_mem == OPP_MEM_DEVICE;
+    k3.humans = dev_out ? b.humans : s.d_humans;
+    k3.n_humans = dev_out ? b.n_humans : s.d_n_humans;
+    k3.flags = d_flags;
+    k3.href_parts = s.d_href_parts, k3.stats = cnt_stats(h, s);
+    k3.thr_vec = 0.05f, k3.thr_human = 0.4f; // THRESH_VECTOR_SCORE, THRESH_HUMAN_SCORE, src/paf.cpp:61,64
+    CU(launch_k3(k3, n, h->k3_smem, st));
+    h->launches += 1;
+
+    // ---- results
+    if (dev_out) {
+        if (b.frame_flags) CU(cudaMemcpyAsync(b.frame_flags, d_flags, n * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    } else {
+        CU(cudaMemcpyAsync(s.h_n_humans, s.d_n_humans, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(s.h_flags, d_flags, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(s.h_humans, s.d_humans, (size_t)n * c.max_humans * sizeof(opp_human_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (forked) {
+        CU(cudaEventRecord(s.ev_join, s.side));
+        CU(cudaStreamWaitEvent(st, s.ev_join, 0));
+    }
+    CU(cudaEventRecord(s.ev_done, st));
+    return OPP_OK;
+}
+
+int opp_submit(opp_handle_t h, const opp_batch_t *b, int *ticket)
+{
+    if (!h || !b || !ticket) return OPP_ERR_INVALID;
+    if (b->n_frames < 1 || b->n_frames > h->cfg.max_batch || !b->conf || !b->paf || !b->humans || !b->n_humans) {
+        set_err(&h->err, "opp_submit: bad batch (n_frames=%d, max_batch=%d)", b->n_frames, h->cfg.max_batch);
+        return OPP_ERR_INVALID;
+    }
+    if ((b->in_mem != OPP_MEM_HOST && b->in_mem != OPP_MEM_DEVICE) || (b->out_mem != OPP_MEM_HOST && b->out_mem != OPP_MEM_DEVICE) ||
+        (b->in_layout != OPP_LAYOUT_CHW && b->in_layout != OPP_LAYOUT_HWC) || (b->up_layout != OPP_LAYOUT_CHW && b->up_layout != OPP_LAYOUT_HWC)) {
+        set_err(&h->err, "opp_submit: bad memory kind or layout");
+        return OPP_ERR_INVALID;
+    }
+    CU(cudaSetDevice(h->device));
+    const int si = h->next_slot;
+    Slot &s = h->slots[si];
+    if (s.busy) {
+        set_err(&h->err, "opp_submit: all %d slots in flight; call opp_wait first", (int)h->slots.size());
+        return OPP_ERR_BUSY;
+    }
+    s.batch = *b, s.n_frames = b->n_frames;
+    const int rc = enqueue(h, s, *b);
+    if (rc != OPP_OK) {
+        cudaStreamSynchronize(s.stream);
+        cudaStreamSynchronize(s.side);
+        cudaGetLastError();
+        return rc;
+    }
+    s.busy = true;
+    s.ticket = h->next_ticket++;
+    *ticket = s.ticket;
+    h->next_slot = (si + 1) % (int)h->slots.size();
+    return OPP_OK;
+}
+
+static Slot *slot_of(opp_handle_s *h, int ticket)
+{
+    for (auto &s : h->slots)
+        if (s.ticket == ticket) return &s;
+    return nullptr;
+}
+
+int opp_wait(opp_handle_t h, int ticket)
+{
+    if (!h) return OPP_ERR_INVALID;
+    Slot *sp = slot_of(h, ticket);
+    if (!sp || !sp->busy) {
+        set_err(&h->err, "opp_wait: unknown ticket %d", ticket);
+        return OPP_ERR_INVALID;
+    }
+    Slot &s = *sp;
+    CU(cudaSetDevice(h->device));
+    cudaError_t e = cudaEventSynchronize(s.ev_done);
+    s.busy = false;
+    if (e != cudaSuccess) {
+        set_err(&h->err, "opp_wait: %s", cudaGetErrorString(e));
+        return OPP_ERR_CUDA;
+    }
+    cudaEventElapsedTime(&s.last_ms, s.ev_start, s.ev_done);
+    const opp_batch_t &b = s.batch;
+    if (b.out_mem == OPP_MEM_HOST) {
+        const int capH = h->cfg.max_humans;
+        std::memcpy(b.n_humans, s.h_n_humans, s.n_frames * sizeof(int));
+        if (b.frame_flags) std::memcpy(b.frame_flags, s.h_flags, s.n_frames * sizeof(int));
+        for (int f = 0; f < s.n_frames; ++f) {
+            const int nh = s.h_n_humans[f] < capH ? s.h_n_humans[f] : capH;
+            if (nh > 0) std::memcpy(b.humans + (size_t)f * capH, s.h_humans + (size_t)f * capH, nh * sizeof(opp_human_t));
+        }
+    }
+    return OPP_OK;
+}
+
+int opp_process(opp_handle_t h, const opp_batch_t *b)
+{
+    int t = -1;
+    int rc = opp_submit(h, b, &t);
+    if (rc != OPP_OK) return rc;
+    return opp_wait(h, t);
+}
+
+float opp_last_batch_ms(opp_handle_t h, int ticket)
+{
+    if (!h) return -1.f;
+    Slot *s = slot_of(h, ticket);
+    return s ? s->last_ms : -1.f;
+}
+
+int64_t opp_launch_count(opp_handle_t h) { return h ? h->launches : 0; }
+
+int opp_debug_fetch(opp_handle_t h, int ticket, int what, int frame, int index, void *dst, int cap)
+{
+    if (!h || !dst) return -1;
+    Slot *sp = slot_of(h, ticket);
+    if (!sp || sp->busy || frame < 0 || frame >= sp->n_frames) return -1;
+    Slot &s = *sp;
+    cudaSetDevice(h->device);
+    const int capP = h->cfg.max_peaks_per_part, capH = h->cfg.max_humans;
+    auto d2h = [&](void *d, const void *src, size_t bytes) { return cudaMemcpy(d, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess; };
+    switch (what) {
+    case OPP_DBG_PEAKS: {
+        int ofs[OPP_N_PARTS + 1];
+        if (!d2h(ofs, s.d_part_ofs + frame * (OPP_N_PARTS + 1), sizeof ofs)) return -1;
+        const int n = ofs[OPP_N_PARTS] < cap ? ofs[OPP_N_PARTS] : cap;
+        if (n > 0 && !d2h(dst, s.d_peaks + (size_t)frame * OPP_N_PARTS * capP, n * sizeof(opp_peak_t))) return -1;
+        return ofs[OPP_N_PARTS];
+    }
+    case OPP_DBG_CONNS: {
+        if (index < 0 || index >= OPP_N_PAIRS) return -1;
+        int n = 0;
+        if (!d2h(&n, s.d_n_conns + frame * OPP_N_PAIRS + index, sizeof n)) return -1;
+        const int m = n < cap ? n : cap;
+        if (m > 0 && !d2h(dst, s.d_conns + ((size_t)frame * OPP_N_PAIRS + index) * capP, m * sizeof(opp_conn_t))) return -1;
+        return n;
+    }
+    case OPP_DBG_PARTS: {
+        if (index < 0 || index >= capH || cap < OPP_N_PARTS) return -1;
+        if (!d2h(dst, s.d_href_parts + ((size_t)frame * capH + index) * OPP_N_PARTS, OPP_N_PARTS * sizeof(int))) return -1;
+        return OPP_N_PARTS;
+    }
+    case OPP_DBG_COUNTS: { // partial humans, merges, accepted candidates, reserved
+        if (cap < 4) return -1;
+        if (!d2h(dst, cnt_stats(h, s) + frame * 4, 4 * sizeof(int))) return -1;
+        return 4;
+    }
+    }
+    return -1;
+}
+
+int opp_resize_device(opp_handle_t h, const float *src, int channels, int n_frames, float *dst, int dst_layout, void *stream)
+{
+    if (!h || !src || !dst || channels < 1 || n_frames < 1) return OPP_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    K1Params k1{};
+    k1.g = h->g, k1.src = src, k1.dst = dst, k1.C = channels, k1.n = n_frames, k1.layout = dst_layout;
+    CU(launch_k1(k1, stream ? (cudaStream_t)stream : h->slots[0].stream));
+    h->launches += 1;
+    return OPP_OK;
+}
+
+static int fill_k2(opp_handle_s *h, Slot &s, const float *conf, const float *conf_up, int n, K2Params &k2)
+{
+    const opp_config_t &c = h->cfg;
+    k2.g = h->g, k2.conf = conf, k2.conf_up = conf_up;
+    k2.capP = c.max_peaks_per_part;
+    k2.cnt.pk_cnt = cnt_pk(h, s), k2.cnt.k2_done = cnt_k2(h, s), k2.cnt.k3_done = cnt_k3(h, s);
+    k2.pk_key = s.d_pk_key, k2.peaks = s.d_peaks, k2.part_ofs = s.d_part_ofs;
+    k2.flags = cnt_flags(h, s);
+    std::memcpy(k2.taps, h->taps, sizeof k2.taps);
+    k2.thresh = 0.05f; // THRESH_HEAT, src/paf.cpp:60
+    if (h->fast_k2) {
+        choose_k2_tiles(h, n, k2.tw, k2.th);
+        k2.nxs = (h->g.w + k2.tw - 1) / k2.tw, k2.nys = (h->g.h + k2.th - 1) / k2.th;
+    }
+    return OPP_OK;
+}
+
+int opp_peaks_device(opp_handle_t h, const float *conf, int n_frames, void *stream)
+{
+    if (!h || !conf || n_frames < 1 || n_frames > h->cfg.max_batch) return OPP_ERR_INVALID;
+    if (!h->fast_k2) {
+        set_err(&h->err, "opp_peaks_device: only the integer-scale peak kernel runs stand-alone");
+        return OPP_ERR_INVALID;
+    }
+    CU(cudaSetDevice(h->device));
+    Slot &s = h->slots[0];
+    if (s.busy) return OPP_ERR_BUSY;
+    cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+    CU(cudaMemsetAsync(s.d_counters, 0, h->counters_ints * sizeof(int), st));
+    K2Params k2{};
+    fill_k2(h, s, conf, nullptr, n_frames, k2);
+    CU(launch_k2_fast(k2, n_frames, st));
+    h->launches += 1;
+    return OPP_OK;
+}
+
+int opp_timer_start(opp_handle_t h)
+{
+    if (!h) return OPP_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    for (auto &s : h->slots) {
+        CU(cudaEventRecord(s.ev_join, s.stream));
+        CU(cudaStreamWaitEvent(h->timer_stream, s.ev_join, 0));
+    }
+    CU(cudaEventRecord(h->timer_t0, h->timer_stream));
+    // work submitted from now on must not start before t0
+    for (auto &s : h->slots) CU(cudaStreamWaitEvent(s.stream, h->timer_t0, 0));
+    return OPP_OK;
+}
+
+float opp_timer_stop(opp_handle_t h)
+{
+    if (!h) return -1.f;
+    cudaSetDevice(h->device);
+    for (auto &s : h->slots) {
+        if (cudaEventRecord(s.ev_join, s.stream) != cudaSuccess) return -1.f;
+        if (cudaStreamWaitEvent(h->timer_stream, s.ev_join, 0) != cudaSuccess) return -1.f;
+    }
+    if (cudaEventRecord(h->timer_t1, h->timer_stream) != cudaSuccess) return -1.f;
+    if (cudaEventSynchronize(h->timer_t1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    cudaEventElapsedTime(&ms, h->timer_t0, h->timer_t1);
+    return ms;
+}
+
+void process_conf_paf(int height, int width, int n_joins_, int n_connections_, const float *peaks_, const float *pafmap_)
+{
+    opp_config_t cfg;
+    opp_config_default(&cfg, height, width, 8 * height, 8 * width, 17);
+    cfg.n_joins = n_joins_, cfg.n_connections = n_connections_, cfg.max_batch = 1, cfg.n_slots = 1;
+    opp_handle_t h = nullptr;
+    if (opp_create(&cfg, &h) != OPP_OK) {
+        fprintf(stderr, "process_conf_paf: %s\n", opp_last_error(nullptr));
+        return;
+    }
+    std::vector<opp_human_t> humans(cfg.max_humans);
+    int n = 0, flags = 0;
+    opp_batch_t b{};
+    b.conf = peaks_, b.paf = pafmap_, b.n_frames = 1, b.in_mem = OPP_MEM_HOST, b.out_mem = OPP_MEM_HOST;
+    b.humans = humans.data(), b.n_humans = &n, b.frame_flags = &flags;
+    if (opp_process(h, &b) != OPP_OK) {
+        fprintf(stderr, "process_conf_paf: %s\n", opp_last_error(h));
+    } else {
+        for (int i = 0; i < n; ++i) { // human_t::print, include/openpose-plus/human.h:21-31
+            for (int j = 0; j < OPP_N_PARTS; ++j) {
+                const opp_body_part_t &bp = humans[i].parts[j];
+                if (bp.has_value) printf("BodyPart:%d-(%.2f, %.2f) score=%.2f ", j, bp.x, bp.y, bp.score);
+            }
+            printf("score=%.2f\n", humans[i].score);
+        }
+    }
+    opp_destroy(h);
+}
+
+} // extern "C"

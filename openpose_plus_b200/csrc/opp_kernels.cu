@@ -1,0 +1,1014 @@
+// Hand-written sm_100a kernels of the openpose-plus post-processing path.
+//
+//   K1  resize        area-mode up-sampling of the 19+38 maps          (src/post-process.h:24-49)
+//   K2  peaks         Gaussian smoothing + 3x3 max NMS + threshold     (src/post-process.h:51-111,155-203)
+//                     + raster-order peak list                          (src/post-process.h:190-198,205-213)
+//   K3  limbs         PAF line-integral scoring of candidate pairs     (src/paf.cpp:79-134,313-337)
+//       matching      std::sort order + greedy bipartite matching      (src/paf.cpp:136-175)
+//       assembly      person assembly + human_t output                 (src/paf.cpp:177-262,292-310)
+//
+// All arithmetic that decides an integer output is written with explicit round-to-nearest
+// intrinsics in the reference's operation order (the library is also built with -fmad=false), so
+// results are bit-identical to a strict-IEEE build of the reference.  No tensor cores: nothing here
+// is a dense contraction.  Citations are relative to /root/reference.
+#include "opp_kernels.cuh"
+
+#include <math_constants.h>
+
+namespace
+{
+// include/openpose-plus/coco.h:11-53
+__constant__ int c_pair_a[OPP_N_PAIRS] = {1, 1, 2, 3, 5, 6, 1, 8, 9, 1, 11, 12, 1, 0, 14, 0, 15, 2, 5};
+__constant__ int c_pair_b[OPP_N_PAIRS] = {2, 5, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 0, 14, 16, 15, 17, 16, 17};
+__constant__ int c_net_x[OPP_N_PAIRS] = {12, 20, 14, 16, 22, 24, 0, 2, 4, 6, 8, 10, 28, 30, 34, 32, 36, 18, 26};
+
+__device__ __forceinline__ int reflect101(int p, int n)
+{
+    // cv::BORDER_REFLECT_101; a single reflection suffices because radius < n is enforced on the host
+    if (p < 0) p = -p;
+    if (p >= n) p = 2 * (n - 1) - p;
+    return p;
+}
+
+__device__ __forceinline__ int clip_idx(int v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); }
+
+// One sample of the area-mode up-sampled map (cv::resize INTER_AREA, dst >= src): horizontal 2-tap
+// on the two source rows, then vertical 2-tap.  Same float operations as the row-buffer form.
+__device__ __forceinline__ float upsample_at(const OppGeom &g, const float *plane, int y, int x)
+{
+    if (g.S > 0) return plane[(y / g.S) * g.w + (x / g.S)];
+    const int sy = g.yofs[y];
+    const float *S0 = plane + clip_idx(sy, g.h) * g.w;
+    const float *S1 = plane + clip_idx(sy + 1, g.h) * g.w;
+    const int sx = g.xofs[x];
+    float r0, r1;
+    if (x < g.xmax) {
+        const float a0 = g.alpha[2 * x], a1 = g.alpha[2 * x + 1];
+        r0 = __fadd_rn(__fmul_rn(S0[sx], a0), __fmul_rn(S0[sx + 1], a1));
+        r1 = __fadd_rn(__fmul_rn(S1[sx], a0), __fmul_rn(S1[sx + 1], a1));
+    } else {
+        r0 = __fmul_rn(S0[sx], 1.f);
+        r1 = __fmul_rn(S1[sx], 1.f);
+    }
+    return __fadd_rn(__fmul_rn(r0, g.beta[2 * y]), __fmul_rn(r1, g.beta[2 * y + 1]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: resize.  Store-bound: 4*C*H*W bytes written per frame against 4*C*h*w read.
+// ------------------------------------------------------------------------------------------------
+
+// Integer scale, CHW, W % 4 == 0, S % 4 == 0: every float4 is one source value replicated.
+// One CTA per (group of source rows, channel, frame); each warp streams whole output rows with
+// 16-byte stores, a warp instruction covering 512 contiguous bytes.
+template <int S>
+__global__ void __launch_bounds__(OPP_THREADS) k1_replicate_chw(const K1Params p, int rows_per_cta)
+{
+    extern __shared__ float s_src[]; // [rows_per_cta][w]
+    const int w = p.g.w, W = p.g.W, h = p.g.h;
+    const int c = blockIdx.y, f = blockIdx.z;
+    const int i0 = blockIdx.x * rows_per_cta;
+    const int i1 = min(i0 + rows_per_cta, h);
+    const float *src = p.src + ((size_t)f * p.C + c) * h * w;
+    for (int t = threadIdx.x; t < (i1 - i0) * w; t += blockDim.x) s_src[t] = __ldg(src + i0 * w + t);
+    __syncthreads();
+    float4 *dst = reinterpret_cast<float4 *>(p.dst + ((size_t)f * p.C + c) * p.g.H * W);
+    const int W4 = W >> 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int y = i0 * S + warp; y < i1 * S; y += nwarps) {
+        const float *row = s_src + (y / S - i0) * w;
+        float4 *drow = dst + (size_t)y * W4;
+        for (int v = lane; v < W4; v += 32) {
+            const float s = row[(v * 4) / S];
+            __stcs(drow + v, make_float4(s, s, s, s));
+        }
+    }
+}
+
+// Any geometry / layout: one thread per output element, table-driven 2x2-tap sample.
+__global__ void __launch_bounds__(OPP_THREADS) k1_general(const K1Params p)
+{
+    const size_t per_frame = (size_t)p.C * p.g.H * p.g.W;
+    const size_t total = per_frame * p.n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i / per_frame);
+        size_t r = i - (size_t)f * per_frame;
+        int c, y, x;
+        if (p.layout == OPP_LAYOUT_CHW) {
+            x = (int)(r % p.g.W), r /= p.g.W;
+            y = (int)(r % p.g.H), c = (int)(r / p.g.H);
+        } else {
+            c = (int)(r % p.C), r /= p.C;
+            x = (int)(r % p.g.W), y = (int)(r / p.g.W);
+        }
+        const float *plane = p.src + ((size_t)f * p.C + c) * p.g.h * p.g.w;
+        __stcs(p.dst + i, upsample_at(p.g, plane, y, x));
+    }
+}
+
+__global__ void __launch_bounds__(OPP_THREADS) k0_hwc_to_chw(const float *src, float *dst, int n, int C, int hw)
+{
+    const size_t total = (size_t)n * C * hw;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int px = (int)(i % hw);
+        const size_t r = i / hw;
+        const int c = (int)(r % C);
+        const size_t f = r / C;
+        dst[i] = __ldg(src + (f * hw + px) * C + c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 shared tail: the last tile of a frame turns the unordered per-part key lists into the
+// reference's all_peaks vector (raster order k -> y -> x, ids = running index).
+// ------------------------------------------------------------------------------------------------
+__device__ void finalize_frame_peaks(const K2Params &p, int frame, int *s_keys /* >= capP ints */)
+{
+    const int W = p.g.W, H = p.g.H;
+    const int capP = p.capP;
+    __shared__ int s_n, s_ofs;
+    if (threadIdx.x == 0) s_ofs = 0;
+    __syncthreads();
+    opp_peak_t *out = p.peaks + (size_t)frame * OPP_N_PARTS * capP;
+    int overflow = 0;
+    for (int part = 0; part < OPP_N_PARTS; ++part) {
+        if (threadIdx.x == 0) {
+            const int raw = __ldcg(p.cnt.pk_cnt + frame * OPP_N_PARTS + part);
+            s_n = raw;
+        }
+        __syncthreads();
+        const int raw = s_n;
+        const int n = min(raw, capP);
+        if (raw > capP) overflow = 1;
+        const int ofs = s_ofs;
+        const int *keys = p.pk_key + ((size_t)frame * OPP_N_PARTS + part) * capP;
+        for (int t = threadIdx.x; t < n; t += blockDim.x) s_keys[t] = __ldcg(keys + t);
+        __syncthreads();
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            const int key = s_keys[t];
+            int rank = 0;
+            for (int u = 0; u < n; ++u) rank += (s_keys[u] < key);
+            const int y = key / W, x = key - y * W;
+            float score;
+            if (p.conf_up)
+                score = __ldcg(p.conf_up + ((size_t)frame * OPP_N_HEAT + part) * H * W + key);
+            else
+                score = upsample_at(p.g, p.conf + ((size_t)frame * OPP_N_HEAT + part) * p.g.h * p.g.w, y, x);
+            opp_peak_t pk;
+            pk.part_id = part, pk.x = x, pk.y = y, pk.score = score, pk.id = ofs + rank;
+            out[ofs + rank] = pk;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            p.part_ofs[frame * (OPP_N_PARTS + 1) + part] = ofs;
+            s_ofs = ofs + n;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        p.part_ofs[frame * (OPP_N_PARTS + 1) + OPP_N_PARTS] = s_ofs;
+        if (overflow) atomicOr(p.flags + frame, OPP_FLAG_PEAK_OVERFLOW);
+    }
+}
+
+__device__ __forceinline__ bool tile_done_is_last(int *counter, int total)
+{
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(counter, 1) == total - 1);
+        __threadfence();
+    }
+    __syncthreads();
+    return s_last != 0;
+}
+
+__device__ __forceinline__ void emit_peak(const K2Params &p, int frame, int part, int y, int x)
+{
+    const int slot = atomicAdd(p.cnt.pk_cnt + frame * OPP_N_PARTS + part, 1);
+    if (slot < p.capP) p.pk_key[((size_t)frame * OPP_N_PARTS + part) * p.capP + slot] = y * p.g.W + x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 fast path: integer scale S, Gaussian radius R <= S.
+//
+// The up-sampled map is S x S blocks of one feature value, so
+//   * the row pass of cv::GaussianBlur only has h distinct input rows (not H): it is evaluated once
+//     per feature row into shared memory (Rrow[h][W]);
+//   * inside one feature row/column the 2R+1 taps touch only three distinct neighbours (a, b, c), so
+//     the tap products are shared between the S phases.  Every product and every sum is still the
+//     same IEEE operation on the same operands in the same order as OpenCV's scalar filter
+//     (row: s = k0*x0; s += kj*xj left to right;  column: s = kR*x; s += k(R+j)*(x[+j] + x[-j])),
+//     so the smoothed map is bit-identical; it never exists in HBM.
+// BORDER_REFLECT_101 at the image edge maps onto the same three neighbours except for the single
+// tap at distance exactly S (only when R == S), handled by the *_sp operands.
+// ------------------------------------------------------------------------------------------------
+template <int S, int R>
+__device__ __forceinline__ void row_taps(const float *__restrict__ k, float a, float b, float c, float a_sp, float c_sp,
+                                         float (&out)[S])
+{
+#pragma unroll
+    for (int q = 0; q < S; ++q) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j <= 2 * R; ++j) {
+            const int o = q + j - R; // offset of the tap from the start of this feature column
+            float v;
+            if (o < 0)
+                v = (R == S && o == -S) ? a_sp : a;
+            else if (o < S)
+                v = b;
+            else
+                v = (R == S && o == 2 * S - 1) ? c_sp : c;
+            const float pr = __fmul_rn(k[j], v);
+            s = (j == 0) ? pr : __fadd_rn(s, pr);
+        }
+        out[q] = s;
+    }
+}
+
+template <int S, int R>
+__device__ __forceinline__ float col_phase(const float *__restrict__ k, const int ph, float a, float b, float c, float a_sp,
+                                           float c_sp)
+{
+    float s = __fmul_rn(k[R], b);
+#pragma unroll
+    for (int j = 1; j <= R; ++j) {
+        const float up = (ph + j < S) ? b : ((R == S && ph == S - 1 && j == R) ? c_sp : c);
+        const float dn = (ph - j >= 0) ? b : ((R == S && ph == 0 && j == R) ? a_sp : a);
+        s = __fadd_rn(s, __fmul_rn(k[R + j], __fadd_rn(up, dn)));
+    }
+    return s;
+}
+
+template <int S, int R>
+__global__ void __launch_bounds__(OPP_THREADS, 2) k2_peaks_fast(const K2Params p)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int frame = blockIdx.z, part = blockIdx.y;
+    const int tx = blockIdx.x % p.nxs, ty = blockIdx.x / p.nxs;
+    const int h = p.g.h, w = p.g.w, W = S * w, H = S * h;
+    const int ja = tx * p.tw, jb = min(ja + p.tw, w);
+    const int ia = ty * p.th, ib = min(ia + p.th, h);
+    const int jlo = max(ja - 1, 0), jhi = min(jb + 1, w);
+    const int ilo = max(ia - 2, 0), ihi = min(ib + 2, h);
+    const int nr = ihi - ilo, ncol = jhi - jlo;
+    const int RW = S * ncol;
+    float *L = smem;                            // [nr][w] feature rows
+    float *Rrow = smem + ((nr * w + 3) & ~3);   // [nr][RW] row-pass result
+    const float *src = p.conf + ((size_t)frame * OPP_N_HEAT + part) * h * w + ilo * w;
+    for (int t = threadIdx.x; t < nr * w; t += blockDim.x) L[t] = __ldg(src + t);
+    __syncthreads();
+
+    // ---- row pass: one thread per (feature row, feature column) -> S outputs
+    for (int it = threadIdx.x; it < nr * ncol; it += blockDim.x) {
+        const int r = it / ncol, c = jlo + (it - r * ncol);
+        const float *Lr = L + r * w;
+        const float b = Lr[c];
+        const float a_raw = Lr[max(c - 1, 0)], c_raw = Lr[min(c + 1, w - 1)];
+        const float a = c > 0 ? a_raw : b, cc = c < w - 1 ? c_raw : b;
+        const float a_sp = c > 0 ? a_raw : c_raw, c_sp = c < w - 1 ? c_raw : a_raw;
+        float out[S];
+        row_taps<S, R>(p.taps, a, b, cc, a_sp, c_sp, out);
+        float *d = Rrow + r * RW + S * (c - jlo);
+        if (S % 4 == 0) {
+#pragma unroll
+            for (int q = 0; q < S; q += 4) *reinterpret_cast<float4 *>(d + q) = make_float4(out[q], out[q + 1], out[q + 2], out[q + 3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < S; ++q) d[q] = out[q];
+        }
+    }
+    __syncthreads();
+
+    // ---- column pass + 3x3 max + threshold: a warp walks down a group of 30 columns (+1 halo each side)
+    const int X0 = S * ja, X1 = S * jb, Y0 = S * ia, Y1 = S * ib;
+    const int xlo = S * jlo, xhi = S * jhi; // columns present in Rrow
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int ngroups = (X1 - X0 + 29) / 30;
+    const float thr = p.thresh;
+    const int i_first = ia > 0 ? ia - 1 : ia, i_last = ib < h ? ib : ib - 1;
+    for (int g = warp; g < ngroups; g += nwarps) {
+        const int x = X0 + 30 * g - 1 + lane;
+        const bool have = x >= xlo && x < xhi;             // column exists (image and staged range)
+        const bool emit_lane = lane >= 1 && lane <= 30 && x < X1;
+        const float *col = Rrow + (have ? x - xlo : 0);
+        float pp_h = -CUDART_INF_F, p_h = -CUDART_INF_F, p_s = -CUDART_INF_F;
+        float va = 0.f, vb, vc;
+        if (i_first > 0) va = col[(i_first - 1 - ilo) * RW];
+        vb = col[(i_first - ilo) * RW];
+        for (int i = i_first; i <= i_last; ++i) {
+            vc = (i < h - 1) ? col[(i + 1 - ilo) * RW] : 0.f;
+            const float a = i > 0 ? va : vb, c = i < h - 1 ? vc : vb;
+            const float a_sp = i > 0 ? va : vc, c_sp = i < h - 1 ? vc : va;
+            const unsigned mask = (i < ia) ? (1u << (S - 1)) : (i >= ib ? 1u : 0xffffffffu);
+#pragma unroll
+            for (int ph = 0; ph < S; ++ph) {
+                if (mask & (1u << ph)) {
+                    const int y = S * i + ph;
+                    const float s = have ? col_phase<S, R>(p.taps + 0, ph, a, vb, c, a_sp, c_sp) : -CUDART_INF_F;
+                    const float l = __shfl_up_sync(0xffffffffu, s, 1);
+                    const float r = __shfl_down_sync(0xffffffffu, s, 1);
+                    const float hm = fmaxf(fmaxf(l, s), r);
+                    const float pooled = fmaxf(fmaxf(pp_h, p_h), hm);
+                    if (p_s > thr && p_s == pooled && emit_lane && y - 1 >= Y0 && y - 1 < Y1) emit_peak(p, frame, part, y - 1, x);
+                    pp_h = p_h, p_h = hm, p_s = s;
+                }
+            }
+            va = vb, vb = vc;
+        }
+        if (ib == h) { // bottom image edge: the row below does not exist
+            const float pooled = fmaxf(pp_h, p_h);
+            if (p_s > thr && p_s == pooled && emit_lane) emit_peak(p, frame, part, H - 1, x);
+        }
+    }
+
+    if (tile_done_is_last(p.cnt.k2_done + frame, p.nxs * p.nys * OPP_N_PARTS))
+        finalize_frame_peaks(p, frame, reinterpret_cast<int *>(smem));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 generic path: any kernel size, any (non-integer) scale.  Reads the materialised up-sampled heat
+// map tile + halo into shared memory with REFLECT_101 indexing, row pass, column pass, 3x3 max.
+// ------------------------------------------------------------------------------------------------
+#define G_TX 64
+#define G_TY 32
+__global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic(const K2Params p)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int frame = blockIdx.z, part = blockIdx.y;
+    const int H = p.g.H, W = p.g.W, K = p.g.K, R = p.g.R;
+    const int tiles_x = (W + G_TX - 1) / G_TX;
+    const int x0 = (blockIdx.x % tiles_x) * G_TX, y0 = (blockIdx.x / tiles_x) * G_TY;
+    const int IW = G_TX + 2 + 2 * R, IH = G_TY + 2 + 2 * R; // input region: outputs + NMS halo + filter halo
+    const int TW = G_TX + 2;
+    float *in = smem;           // [IH][IW]
+    float *tmp = in + IH * IW;  // [IH][TW]  row-pass result
+    float *sm = tmp + IH * TW;  // [G_TY+2][TW] smoothed
+    const float *plane = p.conf_up + ((size_t)frame * OPP_N_HEAT + part) * H * W;
+    // Only pixels inside the image are smoothed; the filter halo reflects, the NMS halo outside the
+    // image is -inf.  Indices of halo pixels whose centre is outside the image are reflected too
+    // (harmless: those smoothed values are discarded).
+    for (int t = threadIdx.x; t < IH * IW; t += blockDim.x) {
+        const int yy = y0 - 1 - R + t / IW, xx = x0 - 1 - R + t % IW;
+        int ry = reflect101(yy, H), rx = reflect101(xx, W);
+        ry = clip_idx(ry, H), rx = clip_idx(rx, W);
+        in[t] = __ldcg(plane + (size_t)ry * W + rx);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < IH * TW; t += blockDim.x) {
+        const int r = t / TW, c = t % TW;      // output column x0-1+c, centred at in[r][c+R]
+        const float *q = in + r * IW + c;      // q[j] = tap j
+        // reflect relative to the *centre* pixel: taps were staged by absolute reflected index, which
+        // is what REFLECT_101 means for an in-image centre.
+        float s;
+        if (K == 3) {
+            s = __fadd_rn(__fmul_rn(q[R], p.taps[R]), __fmul_rn(__fadd_rn(q[R - 1], q[R + 1]), p.taps[R + 1]));
+        } else if (K == 5) {
+            s = __fadd_rn(__fmul_rn(q[R], p.taps[R]), __fmul_rn(__fadd_rn(q[R - 1], q[R + 1]), p.taps[R + 1]));
+            s = __fadd_rn(s, __fmul_rn(__fadd_rn(q[R - 2], q[R + 2]), p.taps[R + 2]));
+        } else {
+            s = __fmul_rn(p.taps[0], q[0]);
+            for (int j = 1; j < K; ++j) s = __fadd_rn(s, __fmul_rn(p.taps[j], q[j]));
+        }
+        tmp[t] = s;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < (G_TY + 2) * TW; t += blockDim.x) {
+        const int r = t / TW, c = t % TW;
+        const int y = y0 - 1 + r, x = x0 - 1 + c;
+        float s = -CUDART_INF_F;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            const float *q = tmp + (r + R) * TW + c;
+            s = __fmul_rn(p.taps[R], q[0]);
+            for (int j = 1; j <= R; ++j) s = __fadd_rn(s, __fmul_rn(p.taps[R + j], __fadd_rn(q[j * TW], q[-j * TW])));
+        }
+        sm[t] = s;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < G_TY * G_TX; t += blockDim.x) {
+        const int r = t / G_TX, c = t % G_TX;
+        const int y = y0 + r, x = x0 + c;
+        if (y >= H || x >= W) continue;
+        const float *q = sm + (r + 1) * TW + (c + 1);
+        const float s = q[0];
+        if (!(s > p.thresh)) continue;
+        float m = fmaxf(fmaxf(q[-TW - 1], q[-TW]), q[-TW + 1]);
+        m = fmaxf(m, fmaxf(fmaxf(q[-1], q[0]), q[1]));
+        m = fmaxf(m, fmaxf(fmaxf(q[TW - 1], q[TW]), q[TW + 1]));
+        if (s == m) emit_peak(p, frame, part, y, x);
+    }
+    if (tile_done_is_last(p.cnt.k2_done + frame, gridDim.x * OPP_N_PARTS)) finalize_frame_peaks(p, frame, reinterpret_cast<int *>(smem));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: one CTA per (limb, frame): score all (a, b) peak pairs, order-preserving compaction of the
+// accepted candidates, std::sort-order sort, greedy matching.  The last limb of a frame to finish
+// assembles the frame's humans.
+// ------------------------------------------------------------------------------------------------
+struct Cand {
+    int i1, i2;
+    float s;
+};
+
+__device__ __forceinline__ bool cand_gt(const Cand &a, const Cand &b) { return a.s > b.s; }
+
+// libstdc++ (GCC 13) std::sort with comp(a,b) = a.score > b.score, as called at src/paf.cpp:151-152.
+// bits/stl_algo.h: __sort :1942, __introsort_loop :1918, __unguarded_partition_pivot :1893,
+// __move_median_to_first :85, __unguarded_partition :1871, __final_insertion_sort :1854,
+// __partial_sort :1905 (heap sort fallback).  Sequential: element movement decides tie order.
+__device__ void sift_down(Cand *first, long hole, long len, Cand value)
+{
+    const long top = hole;
+    long child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (cand_gt(first[child], first[child - 1])) child--;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    long parent = (hole - 1) / 2;
+    while (hole > top && cand_gt(first[parent], value)) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+
+__device__ void heap_sort_range(Cand *first, Cand *last)
+{
+    const long len = last - first;
+    if (len >= 2) {
+        for (long parent = (len - 2) / 2;; --parent) {
+            const Cand v = first[parent];
+            sift_down(first, parent, len, v);
+            if (parent == 0) break;
+        }
+    }
+    while (last - first > 1) {
+        --last;
+        const Cand v = *last;
+        *last = *first;
+        sift_down(first, 0, last - first, v);
+    }
+}
+
+__device__ __forceinline__ void cswap(Cand *a, Cand *b)
+{
+    const Cand t = *a;
+    *a = *b;
+    *b = t;
+}
+
+__device__ void unguarded_linear_insert(Cand *last)
+{
+    const Cand val = *last;
+    Cand *next = last - 1;
+    while (cand_gt(val, *next)) {
+        *last = *next;
+        last = next;
+        --next;
+    }
+    *last = val;
+}
+
+__device__ void insertion_sort_range(Cand *first, Cand *last)
+{
+    if (first == last) return;
+    for (Cand *i = first + 1; i != last; ++i) {
+        if (cand_gt(*i, *first)) {
+            const Cand val = *i;
+            for (Cand *q = i; q != first; --q) *q = *(q - 1);
+            *first = val;
+        } else
+            unguarded_linear_insert(i);
+    }
+}
+
+__device__ void std_sort_desc(Cand *v, int n)
+{
+    if (n <= 0) return;
+    struct Range {
+        int first, last, depth;
+    };
+    Range stack[48];
+    int sp = 0;
+    int lg = 0;
+    for (int t = n; t > 1; t >>= 1) ++lg;
+    stack[sp++] = Range{0, n, 2 * lg};
+    while (sp > 0) {
+        const Range r = stack[--sp];
+        Cand *first = v + r.first, *last = v + r.last;
+        int depth = r.depth;
+        while (last - first > 16) {
+            if (depth == 0) {
+                heap_sort_range(first, last);
+                break;
+            }
+            --depth;
+            Cand *a = first + 1, *b = first + (last - first) / 2, *c = last - 1;
+            // __move_median_to_first(first, a, b, c)
+            if (cand_gt(*a, *b)) {
+                if (cand_gt(*b, *c))
+                    cswap(first, b);
+                else if (cand_gt(*a, *c))
+                    cswap(first, c);
+                else
+                    cswap(first, a);
+            } else if (cand_gt(*a, *c))
+                cswap(first, a);
+            else if (cand_gt(*b, *c))
+                cswap(first, c);
+            else
+                cswap(first, b);
+            // __unguarded_partition(first + 1, last, first)
+            Cand *lo = first + 1, *hi = last;
+            for (;;) {
+                while (cand_gt(*lo, *first)) ++lo;
+                --hi;
+                while (cand_gt(*first, *hi)) --hi;
+                if (!(lo < hi)) break;
+                cswap(lo, hi);
+                ++lo;
+            }
+            // recurse on [lo, last), continue with [first, lo): disjoint ranges, order is immaterial
+            if (sp < 48) stack[sp++] = Range{(int)(lo - v), (int)(last - v), depth};
+            last = lo;
+        }
+    }
+    if (n > 16) {
+        insertion_sort_range(v, v + 16);
+        for (Cand *i = v + 16; i != v + n; ++i) unguarded_linear_insert(i);
+    } else
+        insertion_sort_range(v, v + n);
+}
+
+// words of a partial human (human_ref_t, include/openpose-plus/human.h:57-77)
+#define HR_WORDS 21
+#define HR_ID 0
+#define HR_PART 1
+#define HR_SCORE 19
+#define HR_NPARTS 20
+
+__device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem_raw)
+{
+    int *hr = reinterpret_cast<int *>(smem_raw + p.off_href);     // [capH][21]
+    float *s_score = reinterpret_cast<float *>(smem_raw + p.off_score);
+    opp_conn_t *s_conn = reinterpret_cast<opp_conn_t *>(smem_raw + p.off_conn); // [capP]
+    __shared__ int s_state[8]; // n, hist_max, flags, merges, n_out
+    const int capH = p.capH, capP = p.capP;
+    const int *pofs = p.part_ofs + frame * (OPP_N_PARTS + 1);
+    const int n_peaks = __ldcg(pofs + OPP_N_PARTS);
+    const opp_peak_t *peaks = p.peaks + (size_t)frame * OPP_N_PARTS * capP;
+    if (p.score_in_smem)
+        for (int t = threadIdx.x; t < n_peaks; t += blockDim.x) s_score[t] = __ldcg(&peaks[t].score);
+    if (threadIdx.x < 8) s_state[threadIdx.x] = 0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    int n = 0, hist_max = 0, flags = 0, merges = 0;
+    auto peak_score = [&](int id) -> float {
+        if (id < 0 || id >= n_peaks) {
+            flags |= OPP_FLAG_UB_PEAK_INDEX;
+            return 0.f;
+        }
+        return p.score_in_smem ? s_score[id] : __ldcg(&peaks[id].score);
+    };
+    for (int pair_id = 0; pair_id < OPP_N_PAIRS; ++pair_id) {
+        const int nconn = __ldcg(p.n_conns + frame * OPP_N_PAIRS + pair_id);
+        const opp_conn_t *gconn = p.conns + ((size_t)frame * OPP_N_PAIRS + pair_id) * capP;
+        __syncthreads();
+        for (int t = threadIdx.x; t < nconn; t += blockDim.x) {
+            s_conn[t].cid1 = __ldcg(&gconn[t].cid1);
+            s_conn[t].cid2 = __ldcg(&gconn[t].cid2);
+            s_conn[t].score = __ldcg(&gconn[t].score);
+        }
+        __syncthreads();
+        if (threadIdx.x >= 32) continue; // warp 0 runs the order-dependent part
+        const int part1 = c_pair_a[pair_id], part2 = c_pair_b[pair_id];
+        for (int k = 0; k < nconn; ++k) {
+            const opp_conn_t conn = s_conn[k];
+            // for (auto hr : human_refs) if (hr.touches(...)) hr_ids.push_back(hr.id)   src/paf.cpp:195-199
+            int n_hits = 0, hit0 = -1, hit1 = -1;
+            for (int base = 0; base < n && n_hits < 2; base += 32) {
+                const int q = base + lane;
+                const bool t = q < n && (hr[q * HR_WORDS + HR_PART + part1] == conn.cid1 || hr[q * HR_WORDS + HR_PART + part2] == conn.cid2);
+                unsigned m = __ballot_sync(0xffffffffu, t);
+                while (m && n_hits < 2) {
+                    const int b = __ffs(m) - 1;
+                    const int id = hr[(base + b) * HR_WORDS + HR_ID];
+                    if (n_hits == 0) hit0 = id; else hit1 = id;
+                    ++n_hits;
+                    m &= m - 1;
+                }
+            }
+            if (n_hits == 1) {
+                if (hit0 < 0 || hit0 >= hist_max) {
+                    flags |= OPP_FLAG_UB_STALE_INDEX;
+                } else if (lane == 0) {
+                    int *h1 = hr + hit0 * HR_WORDS;
+                    if (h1[HR_PART + part2] != conn.cid2) {
+                        h1[HR_PART + part2] = conn.cid2;
+                        h1[HR_NPARTS] += 1;
+                        const float sc = __int_as_float(h1[HR_SCORE]);
+                        h1[HR_SCORE] = __float_as_int(__fadd_rn(sc, __fadd_rn(peak_score(conn.cid2), conn.score)));
+                    }
+                }
+                // keep the UB flag warp-uniform
+                flags |= __shfl_sync(0xffffffffu, flags, 0);
+            } else if (n_hits >= 2) {
+                if (hit0 < 0 || hit0 >= hist_max || hit1 < 0 || hit1 >= hist_max) {
+                    flags |= OPP_FLAG_UB_STALE_INDEX;
+                } else {
+                    int *h1 = hr + hit0 * HR_WORDS, *h2 = hr + hit1 * HR_WORDS;
+                    const bool both = lane < OPP_N_PARTS && h1[HR_PART + lane] > 0 && h2[HR_PART + lane] > 0;
+                    const bool membership = __ballot_sync(0xffffffffu, both) != 0;
+                    if (!membership) {
+                        if (lane < OPP_N_PARTS) h1[HR_PART + lane] += h2[HR_PART + lane] + 1;
+                        if (lane == 0) {
+                            h1[HR_NPARTS] += h2[HR_NPARTS];
+                            float sc = __fadd_rn(__int_as_float(h1[HR_SCORE]), __int_as_float(h2[HR_SCORE]));
+                            sc = __fadd_rn(sc, conn.score);
+                            h1[HR_SCORE] = __float_as_int(sc);
+                        }
+                        __syncwarp();
+                        // human_refs.erase(begin() + hr_ids[1])   src/paf.cpp:231
+                        const int e = hit1;
+                        if (e >= n) {
+                            flags |= OPP_FLAG_UB_ERASE_PAST_END; // libstdc++ 13: nothing moves, size shrinks
+                            if (n > 0) --n;
+                        } else {
+                            const int w0 = e * HR_WORDS, w1 = (n - 1) * HR_WORDS;
+                            for (int wbase = w0; wbase < w1; wbase += 32) {
+                                const int wd = wbase + lane;
+                                int v = 0;
+                                if (wd < w1) v = hr[wd + HR_WORDS];
+                                __syncwarp();
+                                if (wd < w1) hr[wd] = v;
+                                __syncwarp();
+                            }
+                            --n;
+                        }
+                        ++merges;
+                    } else if (lane == 0) {
+                        h1[HR_PART + part2] = conn.cid2;
+                        h1[HR_NPARTS] += 1;
+                        const float sc = __int_as_float(h1[HR_SCORE]);
+                        h1[HR_SCORE] = __float_as_int(__fadd_rn(sc, __fadd_rn(peak_score(conn.cid2), conn.score)));
+                    }
+                }
+                flags |= __shfl_sync(0xffffffffu, flags, 0);
+            } else if (pair_id <= 16) { // !is_virtual_pair, include/openpose-plus/coco.h:55
+                if (n >= capH) {
+                    flags |= OPP_FLAG_HUMAN_OVERFLOW;
+                } else {
+                    int *hn = hr + n * HR_WORDS;
+                    if (lane < OPP_N_PARTS) hn[HR_PART + lane] = lane == part1 ? conn.cid1 : (lane == part2 ? conn.cid2 : -1);
+                    if (lane == 0) {
+                        hn[HR_ID] = n;
+                        hn[HR_NPARTS] = 2;
+                        const float sc = __fadd_rn(__fadd_rn(peak_score(conn.cid1), peak_score(conn.cid2)), conn.score);
+                        hn[HR_SCORE] = __float_as_int(sc);
+                    }
+                    flags |= __shfl_sync(0xffffffffu, flags, 0);
+                    ++n;
+                    if (n > hist_max) hist_max = n;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (threadIdx.x == 0) s_state[0] = n, s_state[2] = flags, s_state[3] = merges;
+    __syncthreads();
+    n = s_state[0];
+    // src/paf.cpp:253-260 filter (order kept), :292-310 output
+    opp_human_t *out = p.humans + (size_t)frame * capH;
+    int *out_parts = p.href_parts + (size_t)frame * capH * OPP_N_PARTS;
+    if (threadIdx.x < 32) {
+        int n_out = 0;
+        int uflags = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int q = base + lane;
+            bool keep = false;
+            if (q < n) {
+                const int np = hr[q * HR_WORDS + HR_NPARTS];
+                const float sc = __int_as_float(hr[q * HR_WORDS + HR_SCORE]);
+                keep = !(np < 4 || __fdiv_rn(sc, (float)np) < p.thr_human);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int o = n_out + __popc(m & ((1u << lane) - 1));
+                opp_human_t hu;
+                for (int i = 0; i < OPP_N_PARTS; ++i) {
+                    const int id = hr[q * HR_WORDS + HR_PART + i];
+                    out_parts[o * OPP_N_PARTS + i] = id;
+                    opp_body_part_t bp;
+                    bp.has_value = 0, bp.pad_[0] = bp.pad_[1] = bp.pad_[2] = 0, bp.x = bp.y = bp.score = 0.f;
+                    if (id != -1) {
+                        bp.has_value = 1;
+                        if (id < 0 || id >= n_peaks) {
+                            uflags |= OPP_FLAG_UB_PEAK_INDEX;
+                        } else {
+                            bp.x = (float)__ldcg(&peaks[id].x);
+                            bp.y = (float)__ldcg(&peaks[id].y);
+                            bp.score = __ldcg(&peaks[id].score);
+                        }
+                    }
+                    hu.parts[i] = bp;
+                }
+                hu.score = __int_as_float(hr[q * HR_WORDS + HR_SCORE]);
+                out[o] = hu;
+            }
+            n_out += __popc(m);
+        }
+        for (int o = 16; o > 0; o >>= 1) uflags |= __shfl_xor_sync(0xffffffffu, uflags, o);
+        if (lane == 0) {
+            p.n_humans[frame] = n_out;
+            const int fl = s_state[2] | uflags;
+            if (fl) atomicOr(p.flags + frame, fl);
+            p.stats[frame * 4 + 0] = n;
+            p.stats[frame * 4 + 1] = s_state[3];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const K3Params p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int pair_id = blockIdx.x, frame = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int h = p.g.h, w = p.g.w, capP = p.capP, capC = p.capC;
+    const int pa = c_pair_a[pair_id], pb = c_pair_b[pair_id], cx = c_net_x[pair_id], cy = cx + 1;
+    const int *pofs = p.part_ofs + frame * (OPP_N_PARTS + 1);
+    const int ofs_a = __ldcg(pofs + pa), na = __ldcg(pofs + pa + 1) - ofs_a;
+    const int ofs_b = __ldcg(pofs + pb), nb = __ldcg(pofs + pb + 1) - ofs_b;
+    const opp_peak_t *peaks = p.peaks + (size_t)frame * OPP_N_PARTS * capP;
+
+    float *s_paf = reinterpret_cast<float *>(smem_raw + p.off_paf);      // [2][h*w]
+    int2 *s_pa = reinterpret_cast<int2 *>(smem_raw + p.off_pk);          // [capP]
+    int2 *s_pb = s_pa + capP;                                            // [capP]
+    unsigned char *s_used = smem_raw + p.off_used;                       // [2*capP]
+    int *s_misc = reinterpret_cast<int *>(smem_raw + p.off_misc);        // [16]: warp counts, totals
+    Cand *cand0, *cand1;
+    if (p.cand_in_smem) {
+        cand0 = reinterpret_cast<Cand *>(smem_raw + p.off_cand);
+        cand1 = cand0 + capC;
+    } else {
+        cand0 = reinterpret_cast<Cand *>(p.cand_scratch) + ((size_t)frame * OPP_N_PAIRS + pair_id) * 2 * capC;
+        cand1 = cand0 + capC;
+    }
+
+    int n_cand = 0;
+    const long n_pairs = (long)na * nb;
+    if (n_pairs > 0) {
+        const float *gpx = p.paf + ((size_t)frame * OPP_N_PAF + cx) * h * w;
+        const float *gpy = gpx + h * w;
+        const float *px_plane = gpx, *py_plane = gpy;
+        if (p.paf_in_smem) {
+            for (int t = tid; t < 2 * h * w; t += blockDim.x) s_paf[t] = __ldg(gpx + t);
+            px_plane = s_paf, py_plane = s_paf + h * w;
+        }
+        for (int t = tid; t < na; t += blockDim.x) s_pa[t] = make_int2(__ldcg(&peaks[ofs_a + t].x), __ldcg(&peaks[ofs_a + t].y));
+        for (int t = tid; t < nb; t += blockDim.x) s_pb[t] = make_int2(__ldcg(&peaks[ofs_b + t].x), __ldcg(&peaks[ofs_b + t].y));
+        for (int t = tid; t < 2 * capP; t += blockDim.x) s_used[t] = 0;
+        if (tid < 16) s_misc[tid] = 0;
+        __syncthreads();
+
+        const int H = p.g.H, W = p.g.W;
+        int overflow = 0;
+        for (long base = 0; base < n_pairs; base += blockDim.x) {
+            const long idx = base + tid;
+            bool accept = false;
+            float crit2 = 0.f;
+            int ia = 0, ib = 0;
+            if (idx < n_pairs) {
+                ia = (int)(idx / nb), ib = (int)(idx - (long)ia * nb);
+                const int2 A = s_pa[ia], B = s_pb[ib];
+                const int dx = B.x - A.x, dy = B.y - A.y;
+                const float norm = (float)sqrt((double)(dx * dx + dy * dy)); // src/paf.cpp:91
+                if (!((double)norm < 1e-12)) {
+                    const float vx = __fdiv_rn((float)dx, norm), vy = __fdiv_rn((float)dy, norm);
+                    const float step_x = __fdiv_rn((float)dx, 10.f), step_y = __fdiv_rn((float)dy, 10.f); // :321-322
+                    float scores = 0.f;
+                    int cnt = 0;
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) {
+                        // roundpaf(peak1.x + i * STEP_X): float mul, float add, double +0.5, truncate  :325-326,337
+                        const float fx = __fadd_rn((float)A.x, __fmul_rn((float)i, step_x));
+                        const float fy = __fadd_rn((float)A.y, __fmul_rn((float)i, step_y));
+                        int lx = (int)__dadd_rn((double)fx, 0.5), ly = (int)__dadd_rn((double)fy, 0.5);
+                        lx = clip_idx(lx, W), ly = clip_idx(ly, H);
+                        const float vpx = upsample_at(p.g, px_plane, ly, lx);
+                        const float vpy = upsample_at(p.g, py_plane, ly, lx);
+                        const float score = __fadd_rn(__fmul_rn(vx, vpx), __fmul_rn(vy, vpy)); // :108-109
+                        scores = __fadd_rn(scores, score);
+                        cnt += (score > p.thr_vec);
+                    }
+                    // scores / STEP_PAF + std::min(0.0, 0.5 * height / norm - 1.0)   :115-116
+                    const double pen = __dsub_rn(__ddiv_rn(0.5 * (double)H, (double)norm), 1.0);
+                    crit2 = (float)__dadd_rn((double)__fdiv_rn(scores, 10.f), pen < 0.0 ? pen : 0.0);
+                    accept = cnt > 8 && crit2 > 0.f;
+                }
+            }
+            // order-preserving append (candidates must stay a-major / b-minor: it is std::sort's input order)
+            const unsigned m = __ballot_sync(0xffffffffu, accept);
+            if (lane == 0) s_misc[warp] = __popc(m);
+            __syncthreads();
+            int before = n_cand;
+            for (int q = 0; q < warp; ++q) before += s_misc[q];
+            int total = 0;
+            for (int q = 0; q < nwarps; ++q) total += s_misc[q];
+            if (accept) {
+                const int pos = before + __popc(m & ((1u << lane) - 1));
+                if (pos < capC) {
+                    Cand cd;
+                    cd.i1 = ofs_a + ia, cd.i2 = ofs_b + ib, cd.s = crit2;
+                    cand0[pos] = cd;
+                } else
+                    overflow = 1;
+            }
+            n_cand += total;
+            __syncthreads();
+        }
+        if (__syncthreads_or(overflow)) {
+            if (tid == 0) atomicOr(p.flags + frame, OPP_FLAG_CAND_OVERFLOW);
+            n_cand = min(n_cand, capC);
+        }
+
+        // ---- sort by score, descending, in std::sort's order.  With no equal scores the sorted order is
+        // unique and a parallel rank sort gives it; with ties only the sequential emulation does.
+        Cand *sorted = cand0;
+        if (n_cand > 1) {
+            int tie = 0;
+            if (n_cand <= 4096) {
+                for (int t = tid; t < n_cand; t += blockDim.x) {
+                    const float s = cand0[t].s;
+                    int rank = 0;
+                    for (int u = 0; u < n_cand; ++u) {
+                        const float su = cand0[u].s;
+                        rank += (su > s);
+                        tie |= (su == s && u != t);
+                    }
+                    cand1[rank] = cand0[t];
+                }
+                tie = __syncthreads_or(tie);
+                sorted = cand1;
+            } else
+                tie = 1;
+            if (tie) {
+                sorted = cand0;
+                if (tid == 0) std_sort_desc(cand0, n_cand);
+                __syncthreads();
+            }
+        }
+
+        // ---- greedy matching in sorted order (src/paf.cpp:154-173)
+        if (tid == 0) {
+            opp_conn_t *conns = p.conns + ((size_t)frame * OPP_N_PAIRS + pair_id) * capP;
+            int nc = 0;
+            for (int t = 0; t < n_cand; ++t) {
+                const Cand cd = sorted[t];
+                const int la = cd.i1 - ofs_a, lb = cd.i2 - ofs_b;
+                if (s_used[la] | s_used[capP + lb]) continue;
+                s_used[la] = 1, s_used[capP + lb] = 1;
+                opp_conn_t cn;
+                cn.cid1 = cd.i1, cn.cid2 = cd.i2, cn.score = cd.s;
+                conns[nc++] = cn;
+            }
+            p.n_conns[frame * OPP_N_PAIRS + pair_id] = nc;
+            atomicAdd(p.stats + frame * 4 + 2, n_cand);
+        }
+    } else if (tid == 0) {
+        p.n_conns[frame * OPP_N_PAIRS + pair_id] = 0;
+    }
+
+    if (tile_done_is_last(p.cnt.k3_done + frame, OPP_N_PAIRS)) assemble_frame(p, frame, smem_raw);
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static int g_max_smem = 48 * 1024;
+
+// opt in to the large dynamic shared-memory carve-out (the per-block limit counts static shared memory too)
+template <typename Kern> static cudaError_t allow_big_smem(Kern kern, int *dyn_limit)
+{
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    *dyn_limit = g_max_smem - (int)fa.sharedSizeBytes;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, *dyn_limit);
+}
+
+template <int S, int R>
+static cudaError_t launch_k2_fast_t(const K2Params &p, int n_frames, size_t smem, cudaStream_t st)
+{
+    static int dyn_limit = 0;
+    if (!dyn_limit) {
+        cudaError_t e = allow_big_smem(k2_peaks_fast<S, R>, &dyn_limit);
+        if (e != cudaSuccess) return e;
+    }
+    if (smem > (size_t)dyn_limit) return cudaErrorInvalidValue;
+    dim3 grid(p.nxs * p.nys, OPP_N_PARTS, n_frames);
+    k2_peaks_fast<S, R><<<grid, OPP_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+bool k2_fast_supported(const OppGeom &g)
+{
+    if (g.S != 8 || g.h < 2 || g.w < 2) return false;
+    return g.K == 17 || g.K == 13 || g.K == 9;
+}
+
+size_t k2_fast_smem_bytes(const OppGeom &g, int tw, int th)
+{
+    const int nr = (th + 4 < g.h) ? th + 4 : g.h;
+    const int ncol = (tw + 2 < g.w) ? tw + 2 : g.w;
+    size_t fl = ((size_t)nr * g.w + 3) & ~(size_t)3;
+    fl += (size_t)nr * g.S * ncol;
+    return fl * sizeof(float);
+}
+
+cudaError_t launch_k2_fast(const K2Params &p, int n_frames, cudaStream_t st)
+{
+    const size_t smem = k2_fast_smem_bytes(p.g, p.tw, p.th);
+    size_t need = smem;
+    if ((size_t)p.capP * sizeof(int) > need) need = (size_t)p.capP * sizeof(int);
+    if (need > (size_t)g_max_smem) return cudaErrorInvalidValue;
+    switch (p.g.K) {
+    case 17: return launch_k2_fast_t<8, 8>(p, n_frames, need, st);
+    case 13: return launch_k2_fast_t<8, 6>(p, n_frames, need, st);
+    case 9: return launch_k2_fast_t<8, 4>(p, n_frames, need, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_k2_generic(const K2Params &p, int n_frames, cudaStream_t st)
+{
+    const int R = p.g.R;
+    const int IW = G_TX + 2 + 2 * R, IH = G_TY + 2 + 2 * R, TW = G_TX + 2;
+    size_t smem = ((size_t)IH * IW + (size_t)IH * TW + (size_t)(G_TY + 2) * TW) * sizeof(float);
+    if ((size_t)p.capP * sizeof(int) > smem) smem = (size_t)p.capP * sizeof(int);
+    static int dyn_limit = 0;
+    if (!dyn_limit) {
+        cudaError_t e = allow_big_smem(k2_peaks_generic, &dyn_limit);
+        if (e != cudaSuccess) return e;
+    }
+    if (smem > (size_t)dyn_limit) return cudaErrorInvalidValue;
+    const int tiles = ((p.g.W + G_TX - 1) / G_TX) * ((p.g.H + G_TY - 1) / G_TY);
+    dim3 grid(tiles, OPP_N_PARTS, n_frames);
+    k2_peaks_generic<<<grid, OPP_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k3(const K3Params &p, int n_frames, size_t smem, cudaStream_t st)
+{
+    static int dyn_limit = 0;
+    if (!dyn_limit) {
+        cudaError_t e = allow_big_smem(k3_limbs, &dyn_limit);
+        if (e != cudaSuccess) return e;
+    }
+    if (smem > (size_t)dyn_limit) return cudaErrorInvalidValue;
+    dim3 grid(OPP_N_PAIRS, n_frames);
+    k3_limbs<<<grid, OPP_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k1(const K1Params &p, cudaStream_t st)
+{
+    const OppGeom &g = p.g;
+    const bool aligned = (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0;
+    if (p.layout == OPP_LAYOUT_CHW && g.S == 8 && (g.W & 3) == 0 && aligned) {
+        const int rows = 4; // source rows per CTA -> 32 output rows
+        dim3 grid((g.h + rows - 1) / rows, p.C, p.n);
+        k1_replicate_chw<8><<<grid, OPP_THREADS, rows * g.w * sizeof(float), st>>>(p, rows);
+        return cudaGetLastError();
+    }
+    const size_t total = (size_t)p.n * p.C * g.H * g.W;
+    size_t blocks = (total + OPP_THREADS - 1) / OPP_THREADS;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    k1_general<<<(unsigned)blocks, OPP_THREADS, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hwc_to_chw(const float *src, float *dst, int n, int C, int h, int w, cudaStream_t st)
+{
+    const size_t total = (size_t)n * C * h * w;
+    size_t blocks = (total + OPP_THREADS - 1) / OPP_THREADS;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    k0_hwc_to_chw<<<(unsigned)blocks, OPP_THREADS, 0, st>>>(src, dst, n, C, h * w);
+    return cudaGetLastError();
+}
+
+cudaError_t opp_kernels_init(int max_smem_optin)
+{
+    g_max_smem = max_smem_optin;
+    return cudaSuccess;
+}

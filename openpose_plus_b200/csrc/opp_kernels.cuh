@@ -1,0 +1,85 @@
+// Kernel parameter blocks and launchers of the openpose-plus post-processing path on sm_100a.
+// Reference file:line citations are relative to /root/reference.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/opp_b200.h"
+
+#define OPP_MAX_KSIZE 63
+#define OPP_THREADS 256
+
+// Geometry shared by every stage.  S > 0 means both axes scale by the same integer factor
+// (every configuration in BASELINE.json is x8): INTER_AREA up-sampling is then exact pixel
+// replication and the fast kernels index the feature maps directly.  Otherwise the area-mode
+// coefficient tables (cv::resize, see oracle/opp_oracle.c orc_resize_coeffs) drive a 2x2-tap sample.
+struct OppGeom {
+    int h, w, H, W;
+    int S;
+    int K, R;
+    int xmax;           // first output column whose right tap leaves the source (single tap from there)
+    const int *xofs;    // [W]
+    const float *alpha; // [W][2]
+    const int *yofs;    // [H]
+    const float *beta;  // [H][2]
+};
+
+// frame-level counters, cleared by one memset per batch
+struct OppCounters {
+    int *pk_cnt;  // [n][18] peaks appended per (frame, part)
+    int *k2_done; // [n]     tiles of the frame that finished peak detection
+    int *k3_done; // [n]     limbs of the frame that finished matching
+};
+
+struct K2Params {
+    OppGeom g;
+    const float *conf;    // [n,19,h,w] feature maps
+    const float *conf_up; // [n,19,H,W] materialised maps (generic kernel only)
+    int nxs, nys, tw, th; // tiling in feature-map units (fast kernel) / output tiles (generic)
+    int capP;
+    OppCounters cnt;
+    int *pk_key;          // [n][18][capP] y*W+x, unordered
+    opp_peak_t *peaks;    // [n][18*capP] raster order
+    int *part_ofs;        // [n][19]
+    int *flags;           // [n]
+    float taps[OPP_MAX_KSIZE + 1];
+    float thresh;
+};
+
+struct K3Params {
+    OppGeom g;
+    const float *paf; // [n,38,h,w]
+    const opp_peak_t *peaks;
+    const int *part_ofs;
+    int capP, capC, capH;
+    OppCounters cnt;
+    float *cand_scratch;   // [n][19][2][capC][3] when candidates do not fit shared memory
+    opp_conn_t *conns;     // [n][19][capP]
+    int *n_conns;          // [n][19]
+    opp_human_t *humans;   // [n][capH]
+    int *n_humans;         // [n]
+    int *flags;            // [n]
+    int *href_parts;       // [n][capH][18]
+    int *stats;            // [n][4] partial humans, merges, total candidates, total pairs
+    int paf_in_smem, cand_in_smem, score_in_smem;
+    // shared-memory carve-up (byte offsets)
+    int off_paf, off_pk, off_cand, off_used, off_misc, off_href, off_score, off_conn;
+    float thr_vec, thr_human;
+};
+
+struct K1Params {
+    OppGeom g;
+    const float *src; // [n,C,h,w]
+    float *dst;       // [n,C,H,W] or [n,H,W,C]
+    int C, n;
+    int layout;
+};
+
+size_t k2_fast_smem_bytes(const OppGeom &g, int tw, int th);
+bool k2_fast_supported(const OppGeom &g);
+cudaError_t launch_k2_fast(const K2Params &p, int n_frames, cudaStream_t st);
+cudaError_t launch_k2_generic(const K2Params &p, int n_frames, cudaStream_t st);
+cudaError_t launch_k3(const K3Params &p, int n_frames, size_t smem, cudaStream_t st);
+cudaError_t launch_k1(const K1Params &p, cudaStream_t st);
+cudaError_t launch_hwc_to_chw(const float *src, float *dst, int n, int C, int h, int w, cudaStream_t st);
+cudaError_t opp_kernels_init(int max_smem_optin);
