@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Headline benchmark: post-process frames/sec @368x432 COCO-18 (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one pass of the hot path (resize + smooth/NMS/peaks + limb scoring + matching + assembly)
+over one batch of 64 synthetic 368x432 frames (BASELINE.json configs[1]).  One process per GPU; frames
+shard across ranks with no data-path collective (weak scaling: 64 frames per step per GPU).
+
+  value  frames/s, feature maps already resident in HBM, CUDA-event time over all slot streams,
+         max over ranks.  The up-sampled maps ARE materialised to HBM in this number (the reference
+         keeps them as members, src/paf.cpp:74-75); "fused" reports the skeleton-only mode beside it.
+  e2e    the same through the C-ABI with HOST (pinned) buffers: H2D of the maps and D2H of the
+         skeletons inside the timed region (wall clock between synchronisation points).
+  --impl reference   the reference's own unmodified src/paf.cpp (oracle/_ref, -O3 -ffast-math like its
+         release build) on all host cores, rank 0 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FEAT_H, FEAT_W, STRIDE, KSIZE = 46, 54, 8, 17
+OUT_H, OUT_W = FEAT_H * STRIDE, FEAT_W * STRIDE
+BATCH = 64
+PEOPLE = 5
+# algorithmic bytes per frame
+K1_BYTES_PER_FRAME = 4 * 57 * (FEAT_H * FEAT_W + OUT_H * OUT_W)  # 36 812 880
+K2_BYTES_PER_FRAME = 4 * 19 * OUT_H * OUT_W                      # 12 082 176
+METRIC = "post-process frames/sec @368x432 COCO-18"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(n_batches):
+    """Ring of distinct batches [n_batches][64,...]; 16 rendered frames, rotated differently per batch."""
+    from openpose_plus_b200 import synth
+    conf, paf = synth.render_batch(16, n_people=PEOPLE, feat_h=FEAT_H, feat_w=FEAT_W, stride=STRIDE, seed0=1000)
+    ring = []
+    for b in range(n_batches):
+        idx = [(b * 5 + i) % 16 for i in range(BATCH)]
+        ring.append((np.ascontiguousarray(conf[idx]), np.ascontiguousarray(paf[idx])))
+    return ring
+
+
+def run_reference(args, rank):
+    """The reference's own CPU implementation on all host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle.oracle import Reference, ref_available
+    cores = os.cpu_count() or 1
+    kind = "reference" if ref_available(fast=True) else "port"
+    ring = make_inputs(1)
+    conf, paf = ring[0]
+    geom = (FEAT_H, FEAT_W, OUT_H, OUT_W, KSIZE)
+    if kind == "reference":
+        def step(n):
+            return Reference.time_frames(geom, conf[:n], paf[:n], repeat=1, threads=min(cores, n), fast=True)[0]
+    else:
+        from oracle.oracle import Oracle
+        orc = Oracle(*geom)
+
+        def step(n):
+            t0 = time.perf_counter()
+            for i in range(n):
+                orc.run(conf[i], paf[i], lazy=True)
+            return time.perf_counter() - t0
+        cores = 1
+    # bounded sample: size a step so that steps+warmup finish in about two minutes
+    t1 = step(min(cores, BATCH))
+    per_frame_wall = t1 / min(cores, BATCH)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    n = int(max(min(cores, BATCH), min(BATCH, budget / max(per_frame_wall, 1e-6))))
+    for _ in range(args.warmup):
+        step(n)
+    t = [step(n) for _ in range(args.steps)]
+    total = sum(t)
+    fps = n * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "batch 64 synthetic 368x432 maps (46x54 features, 19 heat + 38 PAF, %d people), gauss 17; reference CPU paf_processor" % PEOPLE,
+                   "frames_per_step": n},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": min(cores, n), "kind": kind,
+                         "sample": "%d frames per step on %d threads, one paf_processor per thread (use_gpu=false)" % (n, min(cores, n))},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slots", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from openpose_plus_b200 import _capi as capi
+    from openpose_plus_b200.engine import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dev = torch.device("cuda", local)
+    RING = 8  # 8 x 36.2 MB of distinct feature maps = 290 MB > 126 MB L2
+    ring = make_inputs(RING)
+    d_ring = [(torch.from_numpy(c).to(dev), torch.from_numpy(p).to(dev)) for c, p in ring]
+    h_ring = []
+    for c, p in ring[:4]:
+        hc, hp = capi.pinned_empty(c.shape, np.float32), capi.pinned_empty(p.shape, np.float32)
+        hc[...] = c
+        hp[...] = p
+        h_ring.append((hc, hp))
+    S = args.slots
+    eng = Engine(FEAT_H, FEAT_W, OUT_H, OUT_W, KSIZE, max_batch=BATCH, device=local, n_slots=S)
+    up = [(torch.empty((BATCH, 19, OUT_H, OUT_W), device=dev), torch.empty((BATCH, 38, OUT_H, OUT_W), device=dev)) for _ in range(S)]
+    outs = [(capi.pinned_empty((BATCH, eng.max_humans), capi.HUMAN_DT), capi.pinned_empty((BATCH,), np.int32), capi.pinned_empty((BATCH,), np.int32)) for _ in range(S)]
+
+    # ---- parity spot check against the oracle before anything is timed (rank 0)
+    parity = None
+    if rank == 0:
+        from oracle.oracle import Oracle
+        orc = Oracle(FEAT_H, FEAT_W, OUT_H, OUT_W, KSIZE)
+        humans, counts, flags = eng.process(d_ring[0][0], d_ring[0][1], conf_up=up[0][0], paf_up=up[0][1])
+        ok = True
+        for f in (0, 1, 2, 3):
+            o = orc.run(ring[0][0][f], ring[0][1][f], maps=(f == 0))
+            g = humans[f, :counts[f]]
+            ok &= counts[f] == o["n_humans"] and all(
+                np.array_equal(np.ascontiguousarray(g["parts"][k]).view(np.uint8), np.ascontiguousarray(o["humans"]["parts"][k]).view(np.uint8)) for k in ("x", "y", "score"))
+            ok &= np.array_equal(g["score"].view(np.uint32), o["humans"]["score"].view(np.uint32))
+            if f == 0:
+                ok &= bool(np.array_equal(up[0][0][0].cpu().numpy(), o["conf_up"])) and bool(np.array_equal(up[0][1][0].cpu().numpy(), o["paf_up"]))
+        parity = bool(ok)
+        if not ok:
+            raise SystemExit("bench.py: CUDA path disagrees with the oracle; refusing to report a number")
+
+    def run_steps(n_steps, mode):
+        """mode: 'materialize' (device maps, up-sampled maps written), 'fused' (device maps, skeletons only),
+        'e2e' (host pinned maps, up-sampled maps written).  Returns frames processed."""
+        inflight = []
+        for k in range(n_steps):
+            s = k % S
+            if len(inflight) == S:
+                eng.wait(inflight.pop(0))
+            if mode == "e2e":
+                c, p = h_ring[k % len(h_ring)]
+            else:
+                c, p = d_ring[k % RING]
+            kw = {} if mode == "fused" else {"conf_up": up[s][0], "paf_up": up[s][1]}
+            inflight.append(eng.submit(c, p, out=outs[s], **kw))
+        for t in inflight:
+            eng.wait(t)
+        return n_steps * BATCH
+
+    def timed(mode, n_steps):
+        run_steps(args.warmup, mode)
+        barrier()
+        l0 = eng.launch_count()
+        eng._check(eng.L.opp_timer_start(eng.h))
+        t0 = time.perf_counter()
+        frames = run_steps(n_steps, mode)
+        dev_ms = float(eng.L.opp_timer_stop(eng.h))
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        launches = eng.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([dev_ms, wall_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dev_ms, wall_ms = float(t[0]), float(t[1])
+        return frames, dev_ms, wall_ms, launches
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    frames, dev_ms, wall_ms, launches = timed("materialize", args.steps)
+    f_frames, f_dev_ms, f_wall_ms, _ = timed("fused", args.steps)
+    e_frames, e_dev_ms, e_wall_ms, _ = timed("e2e", args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- dominant kernels alone, CUDA events on the launching stream (torch's current stream)
+    def time_kernel(fn, iters):
+        st = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream: the launch and both events share it
+        for _ in range(3):
+            fn(0, st.cuda_stream)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for i in range(iters):
+            ev[i][0].record(st)
+            fn(i, st.cuda_stream)
+            ev[i][1].record(st)
+        torch.cuda.synchronize()
+        return statistics.mean(a.elapsed_time(b) for a, b in ev)
+
+    def k1(i, stream):
+        c, p = d_ring[i % RING]
+        eng._check(eng.L.opp_resize_pair_device(eng.h, c.data_ptr(), p.data_ptr(), BATCH, up[i % S][0].data_ptr(), up[i % S][1].data_ptr(),
+                                                 capi.LAYOUT_CHW, stream))
+
+    def k2(i, stream):
+        eng._check(eng.L.opp_peaks_device(eng.h, d_ring[i % RING][0].data_ptr(), BATCH, stream))
+
+    k1_ms = time_kernel(k1, min(max(args.steps, 10), 200))
+    k2_ms = time_kernel(k2, min(max(args.steps, 10), 200))
+    peak, peak_src = measured_peaks()
+    k1_gbs = K1_BYTES_PER_FRAME * BATCH / (k1_ms * 1e-3) / 1e9
+    k2_gbs = K2_BYTES_PER_FRAME * BATCH / (k2_ms * 1e-3) / 1e9
+
+    # ---- p50 latency, one frame, host buffers, submit -> result
+    lat = []
+    one = (h_ring[0][0][:1], h_ring[0][1][:1])
+    for i in range(220):
+        t0 = time.perf_counter()
+        eng.process(one[0], one[1], out=(outs[0][0][:1], outs[0][1][:1], outs[0][2][:1]))
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat_p50 = statistics.median(lat[20:])
+    if world > 1:
+        t = torch.tensor([lat_p50], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lat_p50 = float(t[0])
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.oracle import Reference, ref_available
+        cores = os.cpu_count() or 1
+        if ref_available(fast=True):
+            n = min(BATCH, max(cores, 8))
+            geom = (FEAT_H, FEAT_W, OUT_H, OUT_W, KSIZE)
+            Reference.time_frames(geom, ring[0][0][:min(cores, n)], ring[0][1][:min(cores, n)], 1, min(cores, n), fast=True)
+            rep = 1
+            secs, _ = Reference.time_frames(geom, ring[0][0][:n], ring[0][1][:n], rep, min(cores, n), fast=True)
+            while secs < 8.0 and rep < 64:
+                rep *= 2
+                secs, _ = Reference.time_frames(geom, ring[0][0][:n], ring[0][1][:n], rep, min(cores, n), fast=True)
+            cpu_baseline = {"value": n * rep / secs, "unit": "frames/s", "cores": min(cores, n), "kind": "reference",
+                            "sample": "%d frames x %d passes, reference src/paf.cpp (-O3 -ffast-math) on %d threads, %.1f s" % (n, rep, min(cores, n), secs)}
+        else:
+            from oracle.oracle import Oracle
+            orc = Oracle(FEAT_H, FEAT_W, OUT_H, OUT_W, KSIZE)
+            t0 = time.perf_counter()
+            n = 0
+            while time.perf_counter() - t0 < 10.0:
+                orc.run(ring[0][0][n % BATCH], ring[0][1][n % BATCH], lazy=True)
+                n += 1
+            cpu_baseline = {"value": n / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1, "kind": "port",
+                            "sample": "%d frames, oracle/opp_oracle.c on 1 thread" % n}
+
+    if rank == 0:
+        N = world
+        h2d = BATCH * (19 + 38) * FEAT_H * FEAT_W * 4
+        d2h = BATCH * (eng.max_humans * 292 + 8)
+        line = {
+            "metric": METRIC, "value": N * frames / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": N, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "batch 64 synthetic 368x432 maps (46x54 features, 19 heat + 38 PAF, %d people), gauss 17: resize + smooth/NMS/peaks + limb scoring + matching + assembly, up-sampled maps materialised in HBM" % PEOPLE,
+                       "frames_per_step_per_gpu": BATCH, "slots_in_flight": S,
+                       "l2": "inputs cycle through a ring of %d distinct batches (%.0f MB > 126 MB L2); each step also writes %.0f MB of up-sampled maps" % (RING, RING * h2d / 1e6, BATCH * 57 * OUT_H * OUT_W * 4 / 1e6),
+                       "sharding": "frames sharded over ranks, no collective, host gather"},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "e2e": {"value": N * e_frames / (e_wall_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "device_event_value": N * e_frames / (e_dev_ms * 1e-3), "note": "pinned host maps in, skeletons out, wall clock"},
+            "fused": {"value": N * f_frames / (f_dev_ms * 1e-3), "unit": "frames/s", "note": "skeletons only (C++ paf_processor contract): up-sampled maps never written to HBM"},
+            "latency_ms_p50": lat_p50,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k1_replicate_chw (resize 19+38 maps x8)", "achieved": k1_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": k1_gbs / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": k1_ms,
+                         "algorithmic_bytes_per_frame": K1_BYTES_PER_FRAME},
+            "roofline_k2": {"bound": "hbm", "kernel": "k2_peaks_fast<8,8> (smooth + NMS + peak list)", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
+                            "frac": k2_gbs / peak, "ms_per_launch": k2_ms, "algorithmic_bytes_per_frame": K2_BYTES_PER_FRAME,
+                            "note": "algorithmic bytes = the up-sampled heat map the stage is defined on (SURVEY 8d); the kernel itself is FP32-issue bound and reads only the feature maps"},
+            "clocks": clocks,
+            "parity_checked": parity,
+        }
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -148,6 +148,9 @@ int opp_debug_fetch(opp_handle_t h, int ticket, int what, int frame, int index, 
 /* Stand-alone stages on device memory (used by tests and the bench to time kernels in isolation).
  * stream is a cudaStream_t (NULL = the handle's slot-0 stream). */
 int opp_resize_device(opp_handle_t h, const float *src, int channels, int n_frames, float *dst, int dst_layout, void *stream);
+/* Heat maps and PAFs of n frames in ONE launch (what opp_process issues when both outputs are requested). */
+int opp_resize_pair_device(opp_handle_t h, const float *conf, const float *paf, int n_frames, float *conf_up, float *paf_up, int dst_layout,
+                           void *stream);
 
 /* Peak finding alone (smooth + NMS + raster-order peak list) on device feature maps, on the caller's
  * stream, writing the slot-0 scratch buffers: lets the bench time the kernel with its own events. */

@@ -72,6 +72,11 @@ def lib():
         L.opp_host_free.restype = None
         L.opp_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.opp_resize_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.opp_resize_pair_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.opp_peaks_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.opp_timer_start.argtypes = [C.c_void_p]
+        L.opp_timer_stop.argtypes = [C.c_void_p]
+        L.opp_timer_stop.restype = C.c_float
         L.opp_last_error.argtypes = [C.c_void_p]
         L.opp_last_error.restype = C.c_char_p
         L.opp_version.restype = C.c_char_p
@@ -81,7 +86,7 @@ def lib():
 
 EXPORTS = ["opp_config_default", "opp_create", "opp_destroy", "opp_process", "opp_submit", "opp_wait",
            "opp_last_batch_ms", "opp_launch_count", "opp_host_alloc", "opp_host_free", "opp_debug_fetch",
-           "opp_resize_device", "opp_last_error", "opp_version", "process_conf_paf"]
+           "opp_resize_device", "opp_resize_pair_device", "opp_peaks_device", "opp_timer_start", "opp_timer_stop", "opp_last_error", "opp_version", "process_conf_paf"]
 
 
 def pinned_empty(shape, dtype):

@@ -452,13 +452,23 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
         CU(cudaEventRecord(s.ev_fork, st));
         CU(cudaStreamWaitEvent(s.side, s.ev_fork, 0));
         forked = true;
-        if (b.conf_up && !(generic_needs_conf_up && b.up_layout == OPP_LAYOUT_CHW)) {
-            int r = resize_on(s.side, conf, b.conf_up, OPP_N_HEAT, b.up_layout);
-            if (r) return r;
-        }
-        if (b.paf_up) {
-            int r = resize_on(s.side, paf, b.paf_up, OPP_N_PAF, b.up_layout);
-            if (r) return r;
+        const bool conf_pending = b.conf_up && !(generic_needs_conf_up && b.up_layout == OPP_LAYOUT_CHW);
+        if (conf_pending && b.paf_up) { // both tensors in one launch
+            K1Params k1{};
+            k1.g = g, k1.n = n, k1.layout = b.up_layout;
+            k1.src = conf, k1.dst = b.conf_up, k1.C = OPP_N_HEAT;
+            k1.src2 = paf, k1.dst2 = b.paf_up, k1.C2 = OPP_N_PAF;
+            CU(launch_k1(k1, s.side));
+            h->launches += 1;
+        } else {
+            if (conf_pending) {
+                int r = resize_on(s.side, conf, b.conf_up, OPP_N_HEAT, b.up_layout);
+                if (r) return r;
+            }
+            if (b.paf_up) {
+                int r = resize_on(s.side, paf, b.paf_up, OPP_N_PAF, b.up_layout);
+                if (r) return r;
+            }
         }
     }
 
@@ -656,6 +666,20 @@ static int fill_k2(opp_handle_s *h, Slot &s, const float *conf, const float *con
         choose_k2_tiles(h, n, k2.tw, k2.th);
         k2.nxs = (h->g.w + k2.tw - 1) / k2.tw, k2.nys = (h->g.h + k2.th - 1) / k2.th;
     }
+    return OPP_OK;
+}
+
+int opp_resize_pair_device(opp_handle_t h, const float *conf, const float *paf, int n_frames, float *conf_up, float *paf_up, int dst_layout,
+                           void *stream)
+{
+    if (!h || !conf || !paf || !conf_up || !paf_up || n_frames < 1) return OPP_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    K1Params k1{};
+    k1.g = h->g, k1.n = n_frames, k1.layout = dst_layout;
+    k1.src = conf, k1.dst = conf_up, k1.C = OPP_N_HEAT;
+    k1.src2 = paf, k1.dst2 = paf_up, k1.C2 = OPP_N_PAF;
+    CU(launch_k1(k1, stream ? (cudaStream_t)stream : h->slots[0].stream));
+    h->launches += 1;
     return OPP_OK;
 }
 

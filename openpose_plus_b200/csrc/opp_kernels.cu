@@ -65,13 +65,17 @@ __global__ void __launch_bounds__(OPP_THREADS) k1_replicate_chw(const K1Params p
 {
     extern __shared__ float s_src[]; // [rows_per_cta][w]
     const int w = p.g.w, W = p.g.W, h = p.g.h;
-    const int c = blockIdx.y, f = blockIdx.z;
+    const int f = blockIdx.z;
+    int c = blockIdx.y, C = p.C;
+    const float *src_base = p.src;
+    float *dst_base = p.dst;
+    if (c >= p.C) c -= p.C, C = p.C2, src_base = p.src2, dst_base = p.dst2;
     const int i0 = blockIdx.x * rows_per_cta;
     const int i1 = min(i0 + rows_per_cta, h);
-    const float *src = p.src + ((size_t)f * p.C + c) * h * w;
+    const float *src = src_base + ((size_t)f * C + c) * h * w;
     for (int t = threadIdx.x; t < (i1 - i0) * w; t += blockDim.x) s_src[t] = __ldg(src + i0 * w + t);
     __syncthreads();
-    float4 *dst = reinterpret_cast<float4 *>(p.dst + ((size_t)f * p.C + c) * p.g.H * W);
+    float4 *dst = reinterpret_cast<float4 *>(dst_base + ((size_t)f * C + c) * p.g.H * W);
     const int W4 = W >> 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int y = i0 * S + warp; y < i1 * S; y += nwarps) {
@@ -981,21 +985,37 @@ cudaError_t launch_k3(const K3Params &p, int n_frames, size_t smem, cudaStream_t
     return cudaGetLastError();
 }
 
+static bool k1_fast_ok(const K1Params &p)
+{
+    const OppGeom &g = p.g;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(p.dst) | reinterpret_cast<uintptr_t>(p.dst2)) & 15) == 0;
+    return p.layout == OPP_LAYOUT_CHW && g.S == 8 && (g.W & 3) == 0 && aligned;
+}
+
 cudaError_t launch_k1(const K1Params &p, cudaStream_t st)
 {
     const OppGeom &g = p.g;
-    const bool aligned = (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0;
-    if (p.layout == OPP_LAYOUT_CHW && g.S == 8 && (g.W & 3) == 0 && aligned) {
+    if (k1_fast_ok(p)) {
         const int rows = 4; // source rows per CTA -> 32 output rows
-        dim3 grid((g.h + rows - 1) / rows, p.C, p.n);
+        dim3 grid((g.h + rows - 1) / rows, p.C + p.C2, p.n);
         k1_replicate_chw<8><<<grid, OPP_THREADS, rows * g.w * sizeof(float), st>>>(p, rows);
         return cudaGetLastError();
     }
-    const size_t total = (size_t)p.n * p.C * g.H * g.W;
-    size_t blocks = (total + OPP_THREADS - 1) / OPP_THREADS;
-    if (blocks > 148 * 64) blocks = 148 * 64;
-    k1_general<<<(unsigned)blocks, OPP_THREADS, 0, st>>>(p);
-    return cudaGetLastError();
+    K1Params q = p;
+    for (int part = 0; part < 2; ++part) {
+        if (part == 1) {
+            if (!p.C2) break;
+            q.src = p.src2, q.dst = p.dst2, q.C = p.C2;
+        }
+        q.src2 = nullptr, q.dst2 = nullptr, q.C2 = 0;
+        const size_t total = (size_t)q.n * q.C * g.H * g.W;
+        size_t blocks = (total + OPP_THREADS - 1) / OPP_THREADS;
+        if (blocks > 148 * 64) blocks = 148 * 64;
+        k1_general<<<(unsigned)blocks, OPP_THREADS, 0, st>>>(q);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_hwc_to_chw(const float *src, float *dst, int n, int C, int h, int w, cudaStream_t st)

@@ -73,6 +73,10 @@ struct K1Params {
     float *dst;       // [n,C,H,W] or [n,H,W,C]
     int C, n;
     int layout;
+    // optional second tensor handled by the same launch (heat maps + PAFs in one grid); C2 == 0: none
+    const float *src2;
+    float *dst2;
+    int C2;
 };
 
 size_t k2_fast_smem_bytes(const OppGeom &g, int tw, int th);
