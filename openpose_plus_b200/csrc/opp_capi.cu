@@ -221,15 +221,18 @@ int *cnt_flags(opp_handle_s *h, Slot &s) { return cnt_stats(h, s) + (size_t)h->c
 void choose_k2_tiles(opp_handle_s *h, int n_frames, int &tw, int &th)
 {
     const OppGeom &g = h->g;
-    // column strips of about 240 output columns: 8 groups of 30 columns, one per warp
-    int nxs = (g.W + 239) / 240;
+    // column strips of at most 8 warps x 62 decided columns
+    const int S = g.S > 0 ? g.S : 1;
+    int nxs = (g.W + 62 * 8 - 1) / (62 * 8);
     if (nxs < 1) nxs = 1;
     tw = (g.w + nxs - 1) / nxs;
     th = g.h;
+    (void)S;
+    // two resident CTAs per SM need each to stay under ~110 KB
+    while (k2_fast_smem_bytes(g, tw, th) > (size_t)110 * 1024 && th > 4) th = (th + 1) / 2;
     // small batches: split rows too until the grid covers the chip about twice
     const long want = 2L * h->sm_count;
     while ((long)n_frames * OPP_N_PARTS * ((g.w + tw - 1) / tw) * ((g.h + th - 1) / th) < want && th > 6) th = (th + 1) / 2;
-    while (k2_fast_smem_bytes(g, tw, th) > (size_t)h->max_smem / 2 && th > 4) th = (th + 1) / 2;
     if (h->force_tw > 0) tw = h->force_tw;
     if (h->force_th > 0) th = h->force_th;
 }
@@ -309,7 +312,7 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
         set_err(nullptr, "opp_create: gauss_kernel_size must be odd, 1..%d and smaller than the image", OPP_MAX_KSIZE);
         return OPP_ERR_INVALID;
     }
-    if ((long)OPP_N_PARTS * c.max_peaks_per_part > 1 << 20 || c.max_humans > 8192) {
+    if ((long)OPP_N_PARTS * c.max_peaks_per_part * 4 > 200 * 1024 || c.max_humans > 8192) {
         set_err(nullptr, "opp_create: capacities too large");
         return OPP_ERR_INVALID;
     }

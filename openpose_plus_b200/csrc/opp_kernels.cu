@@ -125,32 +125,37 @@ __global__ void __launch_bounds__(OPP_THREADS) k0_hwc_to_chw(const float *src, f
 // K2 shared tail: the last tile of a frame turns the unordered per-part key lists into the
 // reference's all_peaks vector (raster order k -> y -> x, ids = running index).
 // ------------------------------------------------------------------------------------------------
-__device__ void finalize_frame_peaks(const K2Params &p, int frame, int *s_keys /* >= capP ints */)
+__device__ void finalize_frame_peaks(const K2Params &p, int frame, int *s_keys /* >= 18*capP ints */)
 {
     const int W = p.g.W, H = p.g.H;
     const int capP = p.capP;
-    __shared__ int s_n, s_ofs;
-    if (threadIdx.x == 0) s_ofs = 0;
+    __shared__ int s_n[OPP_N_PARTS], s_ofs[OPP_N_PARTS + 1], s_over;
+    if (threadIdx.x < OPP_N_PARTS) {
+        const int raw = __ldcg(p.cnt.pk_cnt + frame * OPP_N_PARTS + threadIdx.x);
+        s_n[threadIdx.x] = min(raw, capP);
+        if (raw > capP) s_over = 1;
+    }
+    if (threadIdx.x == 32) s_over = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ofs = 0;
+        for (int part = 0; part < OPP_N_PARTS; ++part) s_ofs[part] = ofs, ofs += s_n[part];
+        s_ofs[OPP_N_PARTS] = ofs;
+    }
+    // all keys of the frame in one round trip
+    for (int part = 0; part < OPP_N_PARTS; ++part) {
+        const int *keys = p.pk_key + ((size_t)frame * OPP_N_PARTS + part) * capP;
+        for (int t = threadIdx.x; t < s_n[part]; t += blockDim.x) s_keys[part * capP + t] = __ldcg(keys + t);
+    }
     __syncthreads();
     opp_peak_t *out = p.peaks + (size_t)frame * OPP_N_PARTS * capP;
-    int overflow = 0;
     for (int part = 0; part < OPP_N_PARTS; ++part) {
-        if (threadIdx.x == 0) {
-            const int raw = __ldcg(p.cnt.pk_cnt + frame * OPP_N_PARTS + part);
-            s_n = raw;
-        }
-        __syncthreads();
-        const int raw = s_n;
-        const int n = min(raw, capP);
-        if (raw > capP) overflow = 1;
-        const int ofs = s_ofs;
-        const int *keys = p.pk_key + ((size_t)frame * OPP_N_PARTS + part) * capP;
-        for (int t = threadIdx.x; t < n; t += blockDim.x) s_keys[t] = __ldcg(keys + t);
-        __syncthreads();
+        const int n = s_n[part], ofs = s_ofs[part];
+        const int *k = s_keys + part * capP;
         for (int t = threadIdx.x; t < n; t += blockDim.x) {
-            const int key = s_keys[t];
+            const int key = k[t];
             int rank = 0;
-            for (int u = 0; u < n; ++u) rank += (s_keys[u] < key);
+            for (int u = 0; u < n; ++u) rank += (k[u] < key);
             const int y = key / W, x = key - y * W;
             float score;
             if (p.conf_up)
@@ -161,17 +166,9 @@ __device__ void finalize_frame_peaks(const K2Params &p, int frame, int *s_keys /
             pk.part_id = part, pk.x = x, pk.y = y, pk.score = score, pk.id = ofs + rank;
             out[ofs + rank] = pk;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            p.part_ofs[frame * (OPP_N_PARTS + 1) + part] = ofs;
-            s_ofs = ofs + n;
-        }
-        __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        p.part_ofs[frame * (OPP_N_PARTS + 1) + OPP_N_PARTS] = s_ofs;
-        if (overflow) atomicOr(p.flags + frame, OPP_FLAG_PEAK_OVERFLOW);
-    }
+    if (threadIdx.x <= OPP_N_PARTS) p.part_ofs[frame * (OPP_N_PARTS + 1) + threadIdx.x] = s_ofs[threadIdx.x];
+    if (threadIdx.x == 0 && s_over) atomicOr(p.flags + frame, OPP_FLAG_PEAK_OVERFLOW);
 }
 
 __device__ __forceinline__ bool tile_done_is_last(int *counter, int total)
@@ -246,20 +243,33 @@ __device__ __forceinline__ float col_phase(const float *__restrict__ k, const in
 }
 
 template <int S, int R>
+__device__ __forceinline__ void col_all(const float *__restrict__ k, float a, float b, float c, float a_sp, float c_sp, float (&s)[S])
+{
+#pragma unroll
+    for (int ph = 0; ph < S; ++ph) s[ph] = col_phase<S, R>(k, ph, a, b, c, a_sp, c_sp);
+}
+
+// State of the running 3x3 max for one image column: horizontal 3-max of the two previous rows and
+// the smoothed value of the previous row (the one being decided).
+struct NmsState {
+    float pp_h, p_h, p_s;
+};
+
+template <int S, int R>
 __global__ void __launch_bounds__(OPP_THREADS, 2) k2_peaks_fast(const K2Params p)
 {
     extern __shared__ __align__(16) float smem[];
     const int frame = blockIdx.z, part = blockIdx.y;
     const int tx = blockIdx.x % p.nxs, ty = blockIdx.x / p.nxs;
-    const int h = p.g.h, w = p.g.w, W = S * w, H = S * h;
+    const int h = p.g.h, w = p.g.w, H = S * h;
     const int ja = tx * p.tw, jb = min(ja + p.tw, w);
     const int ia = ty * p.th, ib = min(ia + p.th, h);
     const int jlo = max(ja - 1, 0), jhi = min(jb + 1, w);
     const int ilo = max(ia - 2, 0), ihi = min(ib + 2, h);
     const int nr = ihi - ilo, ncol = jhi - jlo;
     const int RW = S * ncol;
-    float *L = smem;                            // [nr][w] feature rows
-    float *Rrow = smem + ((nr * w + 3) & ~3);   // [nr][RW] row-pass result
+    float *L = smem;                          // [nr][w] feature rows
+    float *Rrow = smem + ((nr * w + 3) & ~3); // [nr][RW] row-pass result
     const float *src = p.conf + ((size_t)frame * OPP_N_HEAT + part) * h * w + ilo * w;
     for (int t = threadIdx.x; t < nr * w; t += blockDim.x) L[t] = __ldg(src + t);
     __syncthreads();
@@ -285,46 +295,87 @@ __global__ void __launch_bounds__(OPP_THREADS, 2) k2_peaks_fast(const K2Params p
     }
     __syncthreads();
 
-    // ---- column pass + 3x3 max + threshold: a warp walks down a group of 30 columns (+1 halo each side)
-    const int X0 = S * ja, X1 = S * jb, Y0 = S * ia, Y1 = S * ib;
+    // ---- column pass + 3x3 max + threshold.  A warp walks down 64 image columns, two per lane: lane l
+    // holds columns xg0-1+2l and xg0+2l, so 62 columns are decided per warp and the outermost two only
+    // feed their neighbours.  Columns that do not exist read -inf, which the filter maps to -inf.
+    const int X0 = S * ja, X1 = S * jb, Y0 = S * ia;
     const int xlo = S * jlo, xhi = S * jhi; // columns present in Rrow
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int ngroups = (X1 - X0 + 29) / 30;
-    const float thr = p.thresh;
-    const int i_first = ia > 0 ? ia - 1 : ia, i_last = ib < h ? ib : ib - 1;
+    const int ngroups = (X1 - X0 + 61) / 62;
+    const float NINF = -CUDART_INF_F;
     for (int g = warp; g < ngroups; g += nwarps) {
-        const int x = X0 + 30 * g - 1 + lane;
-        const bool have = x >= xlo && x < xhi;             // column exists (image and staged range)
-        const bool emit_lane = lane >= 1 && lane <= 30 && x < X1;
-        const float *col = Rrow + (have ? x - xlo : 0);
-        float pp_h = -CUDART_INF_F, p_h = -CUDART_INF_F, p_s = -CUDART_INF_F;
-        float va = 0.f, vb, vc;
-        if (i_first > 0) va = col[(i_first - 1 - ilo) * RW];
-        vb = col[(i_first - ilo) * RW];
-        for (int i = i_first; i <= i_last; ++i) {
-            vc = (i < h - 1) ? col[(i + 1 - ilo) * RW] : 0.f;
-            const float a = i > 0 ? va : vb, c = i < h - 1 ? vc : vb;
-            const float a_sp = i > 0 ? va : vc, c_sp = i < h - 1 ? vc : va;
-            const unsigned mask = (i < ia) ? (1u << (S - 1)) : (i >= ib ? 1u : 0xffffffffu);
-#pragma unroll
-            for (int ph = 0; ph < S; ++ph) {
-                if (mask & (1u << ph)) {
-                    const int y = S * i + ph;
-                    const float s = have ? col_phase<S, R>(p.taps + 0, ph, a, vb, c, a_sp, c_sp) : -CUDART_INF_F;
-                    const float l = __shfl_up_sync(0xffffffffu, s, 1);
-                    const float r = __shfl_down_sync(0xffffffffu, s, 1);
-                    const float hm = fmaxf(fmaxf(l, s), r);
-                    const float pooled = fmaxf(fmaxf(pp_h, p_h), hm);
-                    if (p_s > thr && p_s == pooled && emit_lane && y - 1 >= Y0 && y - 1 < Y1) emit_peak(p, frame, part, y - 1, x);
-                    pp_h = p_h, p_h = hm, p_s = s;
-                }
+        const int x0 = X0 + 62 * g - 1 + 2 * lane, x1 = x0 + 1;
+        const bool have0 = x0 >= xlo && x0 < xhi, have1 = x1 >= xlo && x1 < xhi;
+        const float thr0 = (lane >= 1 && x0 < X1) ? p.thresh : CUDART_INF_F;
+        const float thr1 = (lane <= 30 && x1 < X1) ? p.thresh : CUDART_INF_F;
+        const float *col0 = Rrow + (have0 ? x0 - xlo : 0), *col1 = Rrow + (have1 ? x1 - xlo : 0);
+        NmsState n0 = {NINF, NINF, NINF}, n1 = {NINF, NINF, NINF};
+
+        // one finished image row: decide the row above it.  Decisions are collected as bit masks (bit =
+        // phase of the finished row) and emitted once per feature row: peaks are rare, and one
+        // branch per 8 rows keeps the arithmetic of the 16 running sums in one basic block.
+        unsigned m0 = 0, m1 = 0;
+        auto step = [&](float s0, float s1, int bit, bool decide) {
+            const float l = __shfl_up_sync(0xffffffffu, s1, 1);
+            const float r = __shfl_down_sync(0xffffffffu, s0, 1);
+            const float h0 = fmaxf(fmaxf(l, s0), s1), h1 = fmaxf(fmaxf(s0, s1), r);
+            if (decide) {
+                const bool e0 = n0.p_s > thr0 && n0.p_s >= fmaxf(fmaxf(n0.pp_h, n0.p_h), h0);
+                const bool e1 = n1.p_s > thr1 && n1.p_s >= fmaxf(fmaxf(n1.pp_h, n1.p_h), h1);
+                m0 |= e0 ? (1u << bit) : 0u;
+                m1 |= e1 ? (1u << bit) : 0u;
             }
-            va = vb, vb = vc;
+            n0.pp_h = n0.p_h, n0.p_h = h0, n0.p_s = s0;
+            n1.pp_h = n1.p_h, n1.p_h = h1, n1.p_s = s1;
+        };
+        // bit b set: the row above finished row (y_base + b) is a peak
+        auto flush = [&](int y_base) {
+            if (m0 | m1) {
+                for (unsigned m = m0; m; m &= m - 1) emit_peak(p, frame, part, y_base + __ffs(m) - 2, x0);
+                for (unsigned m = m1; m; m &= m - 1) emit_peak(p, frame, part, y_base + __ffs(m) - 2, x1);
+                m0 = m1 = 0;
+            }
+        };
+        auto ld0 = [&](int i) { return have0 ? col0[(i - ilo) * RW] : NINF; };
+        auto ld1 = [&](int i) { return have1 ? col1[(i - ilo) * RW] : NINF; };
+
+        const int i_first = ia > 0 ? ia - 1 : ia;
+        float a0 = 0.f, a1 = 0.f, b0, b1, c0, c1; // rows i-1, i, i+1 of the two columns
+        if (i_first > 0) a0 = ld0(i_first - 1), a1 = ld1(i_first - 1);
+        b0 = ld0(i_first), b1 = ld1(i_first);
+        float s0[S], s1[S];
+        if (ia > 0) { // halo row above the tile: only its last image row is needed
+            const int i = ia - 1;
+            c0 = ld0(i + 1), c1 = ld1(i + 1); // i + 1 = ia <= h - 1
+            col_all<S, R>(p.taps, i > 0 ? a0 : b0, b0, c0, i > 0 ? a0 : c0, c0, s0);
+            col_all<S, R>(p.taps, i > 0 ? a1 : b1, b1, c1, i > 0 ? a1 : c1, c1, s1);
+            step(s0[S - 1], s1[S - 1], 0, false);
+            n0.p_s = NINF, n1.p_s = NINF; // that row belongs to the tile above
+            a0 = b0, b0 = c0, a1 = b1, b1 = c1;
         }
-        if (ib == h) { // bottom image edge: the row below does not exist
-            const float pooled = fmaxf(pp_h, p_h);
-            if (p_s > thr && p_s == pooled && emit_lane) emit_peak(p, frame, part, H - 1, x);
+        for (int i = ia; i < ib; ++i) {
+            const bool top = i == 0, bot = i == h - 1;
+            c0 = bot ? 0.f : ld0(i + 1), c1 = bot ? 0.f : ld1(i + 1);
+            col_all<S, R>(p.taps, top ? b0 : a0, b0, bot ? b0 : c0, top ? c0 : a0, bot ? a0 : c0, s0);
+            col_all<S, R>(p.taps, top ? b1 : a1, b1, bot ? b1 : c1, top ? c1 : a1, bot ? a1 : c1, s1);
+#pragma unroll
+            for (int ph = 0; ph < S; ++ph) step(s0[ph], s1[ph], ph, true);
+            flush(S * i);
+            a0 = b0, b0 = c0, a1 = b1, b1 = c1;
         }
+        if (ib < h) { // halo row below the tile: its first image row closes the last row of the tile
+            const int i = ib;
+            const bool bot = i == h - 1;
+            c0 = bot ? 0.f : ld0(i + 1), c1 = bot ? 0.f : ld1(i + 1);
+            col_all<S, R>(p.taps, a0, b0, bot ? b0 : c0, a0, bot ? a0 : c0, s0);
+            col_all<S, R>(p.taps, a1, b1, bot ? b1 : c1, a1, bot ? a1 : c1, s1);
+            step(s0[0], s1[0], 0, true);
+            flush(S * i);
+        } else { // bottom image edge: the row below does not exist
+            step(NINF, NINF, 0, true);
+            flush(H);
+        }
+        (void)Y0;
     }
 
     if (tile_done_is_last(p.cnt.k2_done + frame, p.nxs * p.nys * OPP_N_PARTS))
@@ -921,7 +972,9 @@ static cudaError_t launch_k2_fast_t(const K2Params &p, int n_frames, size_t smem
     }
     if (smem > (size_t)dyn_limit) return cudaErrorInvalidValue;
     dim3 grid(p.nxs * p.nys, OPP_N_PARTS, n_frames);
-    k2_peaks_fast<S, R><<<grid, OPP_THREADS, smem, st>>>(p);
+    const int groups = (S * p.tw + 61) / 62;
+    const int threads = 32 * (groups < 1 ? 1 : (groups > OPP_THREADS / 32 ? OPP_THREADS / 32 : groups));
+    k2_peaks_fast<S, R><<<grid, threads, smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -944,7 +997,7 @@ cudaError_t launch_k2_fast(const K2Params &p, int n_frames, cudaStream_t st)
 {
     const size_t smem = k2_fast_smem_bytes(p.g, p.tw, p.th);
     size_t need = smem;
-    if ((size_t)p.capP * sizeof(int) > need) need = (size_t)p.capP * sizeof(int);
+    if ((size_t)OPP_N_PARTS * p.capP * sizeof(int) > need) need = (size_t)OPP_N_PARTS * p.capP * sizeof(int);
     if (need > (size_t)g_max_smem) return cudaErrorInvalidValue;
     switch (p.g.K) {
     case 17: return launch_k2_fast_t<8, 8>(p, n_frames, need, st);
@@ -959,7 +1012,7 @@ cudaError_t launch_k2_generic(const K2Params &p, int n_frames, cudaStream_t st)
     const int R = p.g.R;
     const int IW = G_TX + 2 + 2 * R, IH = G_TY + 2 + 2 * R, TW = G_TX + 2;
     size_t smem = ((size_t)IH * IW + (size_t)IH * TW + (size_t)(G_TY + 2) * TW) * sizeof(float);
-    if ((size_t)p.capP * sizeof(int) > smem) smem = (size_t)p.capP * sizeof(int);
+    if ((size_t)OPP_N_PARTS * p.capP * sizeof(int) > smem) smem = (size_t)OPP_N_PARTS * p.capP * sizeof(int);
     static int dyn_limit = 0;
     if (!dyn_limit) {
         cudaError_t e = allow_big_smem(k2_peaks_generic, &dyn_limit);
