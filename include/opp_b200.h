@@ -130,6 +130,8 @@ int opp_wait(opp_handle_t h, int ticket);
 
 /* Device time (ms, CUDA events on the slot's stream) of the last completed batch on a ticket's slot. */
 float opp_last_batch_ms(opp_handle_t h, int ticket);
+/* CUDA ordinal the handle lives on (resolves device = -1). */
+int opp_device(opp_handle_t h);
 /* Number of kernel launches issued by this handle so far. */
 int64_t opp_launch_count(opp_handle_t h);
 

@@ -64,6 +64,7 @@ def lib():
         L.opp_wait.argtypes = [C.c_void_p, C.c_int]
         L.opp_last_batch_ms.argtypes = [C.c_void_p, C.c_int]
         L.opp_last_batch_ms.restype = C.c_float
+        L.opp_device.argtypes = [C.c_void_p]
         L.opp_launch_count.argtypes = [C.c_void_p]
         L.opp_launch_count.restype = C.c_int64
         L.opp_host_alloc.argtypes = [C.c_size_t]
@@ -85,7 +86,7 @@ def lib():
 
 
 EXPORTS = ["opp_config_default", "opp_create", "opp_destroy", "opp_process", "opp_submit", "opp_wait",
-           "opp_last_batch_ms", "opp_launch_count", "opp_host_alloc", "opp_host_free", "opp_debug_fetch",
+           "opp_last_batch_ms", "opp_launch_count", "opp_device", "opp_host_alloc", "opp_host_free", "opp_debug_fetch",
            "opp_resize_device", "opp_resize_pair_device", "opp_peaks_device", "opp_timer_start", "opp_timer_stop", "opp_last_error", "opp_version", "process_conf_paf"]
 
 

@@ -605,6 +605,8 @@ float opp_last_batch_ms(opp_handle_t h, int ticket)
 
 int64_t opp_launch_count(opp_handle_t h) { return h ? h->launches : 0; }
 
+int opp_device(opp_handle_t h) { return h ? h->device : -1; }
+
 int opp_debug_fetch(opp_handle_t h, int ticket, int what, int frame, int index, void *dst, int cap)
 {
     if (!h || !dst) return -1;

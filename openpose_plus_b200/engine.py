@@ -41,6 +41,7 @@ class Engine:
         rc = self.L.opp_create(C.byref(cfg), C.byref(self.h))
         if rc != capi.OK:
             raise capi.OppError(rc, (self.L.opp_last_error(None) or b"").decode())
+        self.device = int(self.L.opp_device(self.h))
         self.feat = (feat_h, feat_w)
         self.out = (out_h, out_w)
         self.max_batch, self.max_humans = max_batch, max_humans

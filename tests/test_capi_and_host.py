@@ -1,0 +1,156 @@
+"""CPU: the C-ABI library loads and exports everything include/opp_b200.h declares (no compute calls
+without a GPU), struct layouts match the reference's, and the host-side logic (result conversion,
+sharding, gather over gloo with world_size 2)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import conftest
+from openpose_plus_b200 import _capi as capi
+
+ROOT = conftest.ROOT
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "opp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set(re.findall(r"\b(opp_[a-z_0-9]+|process_conf_paf)\s*\(", src))
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.lib()
+    names = declared_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), n
+    assert set(capi.EXPORTS) == set(names)
+    assert b"sm_100a" in L.opp_version()
+
+
+def test_struct_layouts():
+    assert capi.HUMAN_DT.itemsize == 292 and capi.PEAK_DT.itemsize == 20 and capi.CONN_DT.itemsize == 12
+    assert C.sizeof(capi.Config) == 16 * 4
+    assert C.sizeof(capi.Batch) == 2 * 8 + 4 * 4 + 3 * 8 + 2 * 8 + 4 * 4
+
+
+@pytest.mark.skipif(conftest.HAS_GPU, reason="only meaningful without a GPU")
+def test_create_fails_loudly_without_gpu():
+    from openpose_plus_b200.engine import Engine
+    with pytest.raises(capi.OppError) as e:
+        Engine(46, 54)
+    assert e.value.code == capi.ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "openpose_plus_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                for pat in (r"^\s*(from|import)\s+oracle", r"liborc", r"libopp_ref", r"#include\s*[<\"][^>\"]*oracle", r"orc_[a-z_]+\s*\("):
+                    assert not re.search(pat, text, re.M), (os.path.join(dirpath, f), pat)
+
+
+def test_cpp_dropin_header_compiles_and_links():
+    """A caller written against the reference's API (create_paf_processor / paf_processor / human_t)
+    builds against include/ and links with the library."""
+    src = r'''
+#include <memory>
+#include <openpose-plus.h>
+static_assert(sizeof(human_t) == 292, "human_t");
+int main(int argc, char **) {
+    if (argc > 100) {
+        std::unique_ptr<paf_processor> p(create_paf_processor(46, 54, 368, 432, n_joins, n_connections, 17));
+        std::vector<human_t> hs = (*p)(nullptr, nullptr, true);
+        for (const auto &h : hs) h.print();
+        process_conf_paf(46, 54, n_joins, n_connections, nullptr, nullptr);
+    }
+    return COCOPAIRS.size() == 19 && COCOPAIRS_NET.size() == 19 && is_virtual_pair(17) ? 0 : 1;
+}
+'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        cpp, exe = os.path.join(d, "t.cpp"), os.path.join(d, "t")
+        open(cpp, "w").write(src)
+        libdir = os.path.join(ROOT, "openpose_plus_b200")
+        cmd = ["g++", "-std=c++14", "-I", os.path.join(ROOT, "include"), cpp, "-o", exe, "-L", libdir, "-l:libopp_b200.so",
+               "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert subprocess.run([exe]).returncode == 0
+
+
+def test_humans_from_records_normalises_like_the_reference():
+    from openpose_plus_b200.post_process import humans_from_records
+    rec = np.zeros(2, capi.HUMAN_DT)
+    rec[0]["score"] = 3.5
+    rec[0]["parts"][1] = (1, [0, 0, 0], 216.0, 92.0, 0.9)
+    rec[0]["parts"][4] = (1, [0, 0, 0], 0.0, 367.0, 0.5)
+    hs = humans_from_records(rec, 368, 432)
+    assert len(hs) == 1 and set(hs[0].body_parts) == {1, 4}
+    bp = hs[0].body_parts[1]
+    assert (bp.x, bp.y, bp.uidx, bp.part_idx) == (0.5, 0.25, "0-1", 1) and abs(bp.score - 0.9) < 1e-6
+    assert hs[0].score == 3.5 and str(bp).startswith("BodyPart:1-(0.50, 0.25)")
+
+
+def test_shard_ranges_partition_the_stream():
+    from openpose_plus_b200.sharding import shard_range
+    for n in (0, 1, 7, 64, 4096, 4097):
+        for world in (1, 2, 3, 4, 8):
+            r = [shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_synth_is_deterministic_and_in_range():
+    from openpose_plus_b200 import synth
+    a, b = synth.render_frame(42, 3), synth.render_frame(42, 3)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert a[0].shape == (19, 46, 54) and a[1].shape == (38, 46, 54)
+    assert a[0].min() >= 0 and a[0].max() <= 1 and np.abs(a[1]).max() <= 1
+    assert a[0][:18].max() > 0.5
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from openpose_plus_b200 import _capi as capi
+from openpose_plus_b200.sharding import shard_range, gather_results
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+n = 37
+lo, hi = shard_range(n, rank, world)
+humans = np.zeros((hi - lo, 4), capi.HUMAN_DT)
+counts = np.arange(lo, hi, dtype=np.int32) % 4
+flags = np.zeros(hi - lo, np.int32)
+for f in range(lo, hi):
+    humans[f - lo]["score"] = f          # frame index rides in the payload
+res = gather_results((humans, counts, flags), rank, world)
+if rank == 0:
+    H, Cn, F = res
+    assert H.shape == (n, 4) and np.array_equal(H["score"][:, 0], np.arange(n, dtype=np.float32))
+    assert np.array_equal(Cn, np.arange(n, dtype=np.int32) % 4)
+    print("GATHER_OK")
+else:
+    assert res is None
+dist.destroy_process_group()
+'''
+
+
+def test_host_gather_world_size_2_gloo(tmp_path):
+    w = tmp_path / "worker.py"
+    w.write_text(_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", str(w), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "GATHER_OK" in r.stdout, r.stdout + r.stderr

@@ -1,0 +1,122 @@
+"""-m gpu: the CUDA path against the committed golden vectors (reference build outputs), the
+batched / pipelined / sharded host drivers, materialised maps, channels-last input, and
+size-independent properties at BASELINE.json's full sizes."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from openpose_plus_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FRAMES = sorted(glob.glob(os.path.join(GOLD, "frame_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from openpose_plus_b200.engine import Engine
+    from openpose_plus_b200 import _capi as capi
+    import helpers
+    return Engine, capi, helpers
+
+
+@pytest.mark.parametrize("path", FRAMES, ids=[os.path.basename(p)[:-4] for p in FRAMES])
+def test_cuda_reproduces_reference_golden(mods, path):
+    Engine, capi, H = mods
+    g = np.load(path)
+    h, w, oh, ow, k = [int(v) for v in g["geom"]]
+    eng = Engine(h, w, oh, ow, k, max_batch=1, max_peaks_per_part=512, max_cands_per_limb=8192, max_humans=512)
+    t = eng.submit(g["conf"][None], g["paf"][None])
+    humans, counts, flags = eng.wait(t)
+    assert (flags[0] & capi.FLAG_OVERFLOW_MASK) == 0
+    assert np.array_equal(eng.debug_peaks(t, 0, cap=18 * 512).view(np.uint8), g["peaks"].view(np.uint8))
+    for p in range(19):
+        assert np.array_equal(eng.debug_conns(t, 0, p).view(np.uint8), g["conns_%02d" % p].view(np.uint8)), p
+    assert H.humans_equal(humans[0, :counts[0]], g["humans_ref"]) is None
+    for i in range(counts[0]):
+        assert np.array_equal(eng.debug_parts(t, 0, i), g["hrefs"]["parts"][i])
+
+
+def test_materialised_maps_and_layouts(mods):
+    import torch
+    from oracle.oracle import Oracle
+    Engine, capi, H = mods
+    conf, paf = synth.render_batch(3, n_people=4, seed0=70)
+    for (oh, ow) in [(368, 432), (300, 400)]:
+        eng, orc = Engine(46, 54, oh, ow, 17, max_batch=3), Oracle(46, 54, oh, ow, 17)
+        cu = torch.empty((3, 19, oh, ow), device="cuda")
+        pu = torch.empty((3, 38, oh, ow), device="cuda")
+        humans, counts, flags = eng.process(conf, paf, conf_up=cu, paf_up=pu)
+        cu2 = torch.empty((3, oh, ow, 19), device="cuda")
+        pu2 = torch.empty((3, oh, ow, 38), device="cuda")
+        # channels-last in, channels-last maps out (the Python PostProcessor contract)
+        h2, c2, f2 = eng.process(np.ascontiguousarray(conf.transpose(0, 2, 3, 1)), np.ascontiguousarray(paf.transpose(0, 2, 3, 1)),
+                                 layout=capi.LAYOUT_HWC, conf_up=cu2, paf_up=pu2, up_layout=capi.LAYOUT_HWC)
+        assert np.array_equal(counts, c2)
+        for f in range(3):
+            o = orc.run(conf[f], paf[f], maps=True)
+            assert np.array_equal(cu[f].cpu().numpy(), o["conf_up"]) and np.array_equal(pu[f].cpu().numpy(), o["paf_up"])
+            assert np.array_equal(cu2[f].cpu().numpy(), o["conf_up"].transpose(1, 2, 0))
+            assert np.array_equal(pu2[f].cpu().numpy(), o["paf_up"].transpose(1, 2, 0))
+            assert H.humans_equal(humans[f, :counts[f]], o["humans"]) is None
+            assert H.humans_equal(h2[f, :c2[f]], o["humans"]) is None
+
+
+def test_device_resident_inputs_and_pipelined_stream(mods):
+    """4096-frame stream (BASELINE configs[4]) through submit/wait with all slots in flight, device
+    inputs; properties: every frame equals the result of its source frame processed alone."""
+    import torch
+    from openpose_plus_b200.sharding import process_stream
+    Engine, capi, H = mods
+    base_c, base_p = synth.render_batch(16, n_people=5, seed0=500)
+    idx = np.arange(4096) % 16
+    conf = torch.from_numpy(base_c).cuda()[torch.from_numpy(idx).cuda()]
+    paf = torch.from_numpy(base_p).cuda()[torch.from_numpy(idx).cuda()]
+    eng = Engine(46, 54, max_batch=64)
+    humans, counts, flags = process_stream(eng, conf, paf)
+    ref_h, ref_c, ref_f = eng.process(base_c, base_p)
+    assert not (flags & capi.FLAG_OVERFLOW_MASK).any()
+    assert np.array_equal(counts, ref_c[idx]) and np.array_equal(flags, ref_f[idx])
+    for f in range(0, 4096, 97):
+        assert H.humans_equal(humans[f, :counts[f]], ref_h[idx[f], :ref_c[idx[f]]]) is None
+
+
+def test_python_postprocessor_dropin(mods):
+    from oracle.oracle import Oracle
+    from openpose_plus_b200 import PostProcessor
+    conf, paf = synth.render_frame(77, 4)
+    orc = Oracle(46, 54, 368, 432, 17).run(conf, paf, maps=True)
+    for fmt in ("channels_first", "channels_last"):
+        pp = PostProcessor((368, 432), (46, 54), fmt)
+        hm, pm = (conf, paf) if fmt == "channels_first" else (conf.transpose(1, 2, 0), paf.transpose(1, 2, 0))
+        humans, hup, pup = pp(hm, pm)
+        assert hup.shape == (368, 432, 19) and pup.shape == (368, 432, 38)
+        assert np.array_equal(hup, orc["conf_up"].transpose(1, 2, 0)) and np.array_equal(pup, orc["paf_up"].transpose(1, 2, 0))
+        assert len(humans) == orc["n_humans"]
+        for hu, rec in zip(humans, orc["humans"]):
+            assert abs(hu.score - rec["score"]) <= 1e-5 * abs(rec["score"])
+            for idx, bp in hu.body_parts.items():
+                assert rec["parts"][idx]["has_value"]
+                assert bp.x == rec["parts"][idx]["x"] / 432 and bp.y == rec["parts"][idx]["y"] / 368
+
+
+def test_capacity_overflow_is_flagged_not_silent(mods):
+    Engine, capi, H = mods
+    conf, paf = synth.noise_frame(3)
+    eng = Engine(46, 54, max_batch=1)
+    humans, counts, flags = eng.process(conf[None], paf[None])
+    assert flags[0] & capi.FLAG_PEAK_OVERFLOW
+
+
+def test_bad_arguments_are_errors(mods):
+    Engine, capi, H = mods
+    with pytest.raises(capi.OppError):
+        Engine(46, 54, 20, 432)          # down-sampling is not INTER_AREA up-sampling
+    with pytest.raises(capi.OppError):
+        Engine(46, 54, gauss_kernel_size=16)
+    eng = Engine(46, 54, max_batch=2)
+    conf, paf = synth.render_batch(3, n_people=1)
+    with pytest.raises(capi.OppError):
+        eng.process(conf, paf)           # more frames than max_batch

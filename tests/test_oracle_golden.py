@@ -1,0 +1,98 @@
+"""CPU: the oracle (plain-C restatement) against the committed golden vectors minted from the
+reference's own build and cv2 (scripts/make_golden.py), and against the live reference build / cv2
+where they are present in the container."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle, Reference, CAND_DT, ref_available
+import helpers
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FRAMES = sorted(glob.glob(os.path.join(GOLD, "frame_*.npz")))
+
+
+def test_golden_present():
+    assert len(FRAMES) >= 8 and os.path.exists(os.path.join(GOLD, "opencv_pieces.npz"))
+
+
+@pytest.mark.parametrize("path", FRAMES, ids=[os.path.basename(p)[:-4] for p in FRAMES])
+def test_oracle_reproduces_reference_humans(path):
+    g = np.load(path)
+    h, w, H, W, k = [int(v) for v in g["geom"]]
+    o = Oracle(h, w, H, W, k).run(g["conf"], g["paf"])
+    assert helpers.humans_equal(o["humans"], g["humans_ref"]) is None
+    assert np.array_equal(o["peaks"], g["peaks"])
+    for p in range(19):
+        assert np.array_equal(o["conns"][p], g["conns_%02d" % p])
+    assert np.array_equal(o["hrefs"]["parts"], g["hrefs"]["parts"])
+    assert [o["n_incomplete"], o["n_merges"], o["flags"]] == g["counts"].tolist()
+    # the lazy mode (PAF sampled on demand instead of materialised) is the same arithmetic
+    ol = Oracle(h, w, H, W, k).run(g["conf"], g["paf"], lazy=True)
+    assert helpers.humans_equal(ol["humans"], g["humans_ref"]) is None
+
+
+def test_opencv_pieces_bit_exact():
+    g = np.load(os.path.join(GOLD, "opencv_pieces.npz"))
+    for k in range(1, 64, 2):
+        assert np.array_equal(Oracle.gauss_kernel(k), g["taps_%d" % k]), k
+    src = g["resize_src"]
+    for key in g.files:
+        if key.startswith("resize_") and key != "resize_src":
+            H, W = [int(v) for v in key[7:].split("x")]
+            assert np.array_equal(Oracle.resize_area(src, H, W), g[key]), key
+    for k in (1, 3, 5, 7, 9, 13, 17, 25, 31):
+        assert np.array_equal(Oracle.gauss_blur(g["blur_src"], k), g["blur_%d" % k]), k
+        assert np.array_equal(Oracle.gauss_blur(g["blur_src2"], k), g["blur2_%d" % k]), k
+    assert np.array_equal(Oracle.max_pool(g["blur_src2"]), g["dilate"])
+
+
+def test_x8_upsample_is_replication():
+    rng = np.random.default_rng(3)
+    a = rng.random((46, 54), dtype=np.float32)
+    assert np.array_equal(Oracle.resize_area(a, 368, 432), np.repeat(np.repeat(a, 8, 0), 8, 1))
+
+
+def test_against_live_cv2():
+    cv2 = pytest.importorskip("cv2")
+    cv2.ipp.setUseIPP(False)
+    cv2.setUseOptimized(False)
+    cv2.setNumThreads(1)
+    rng = np.random.default_rng(5)
+    a = (rng.random((31, 29), dtype=np.float32) * 2 - 1).astype(np.float32)
+    for (H, W) in [(248, 232), (100, 97), (31, 58), (63, 30)]:
+        assert np.array_equal(Oracle.resize_area(a, H, W), cv2.resize(a, (W, H), interpolation=cv2.INTER_AREA))
+    b = rng.random((64, 80), dtype=np.float32)
+    for k in (3, 5, 9, 17, 21):
+        assert np.array_equal(Oracle.gauss_blur(b, k), cv2.GaussianBlur(b, (k, k), 3.0))
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_std_sort_emulation_matches_libstdcxx():
+    rng = np.random.default_rng(1)
+    for n in list(range(0, 40)) + [100, 257, 1000, 5000]:
+        for trial in range(4):
+            v = np.zeros(n, CAND_DT)
+            v["idx1"] = np.arange(n)
+            v["idx2"] = rng.integers(0, 50, n)
+            nd = [max(1, n), max(1, n // 4), 3, 1][trial]
+            v["score"] = rng.integers(0, nd, n).astype(np.float32) / 7
+            assert np.array_equal(Oracle.std_sort_desc(v), Reference.std_sort_desc(v)), (n, trial)
+    for n in (1000, 4096):  # patterns that push introsort towards its depth limit
+        for arr in (np.arange(n), np.arange(n)[::-1], np.concatenate([np.arange(n // 2), np.arange(n // 2)[::-1]])):
+            v = np.zeros(n, CAND_DT)
+            v["idx1"] = np.arange(n)
+            v["score"] = arr.astype(np.float32)
+            assert np.array_equal(Oracle.std_sort_desc(v), Reference.std_sort_desc(v))
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_matches_live_reference_on_fresh_frames():
+    from openpose_plus_b200 import synth
+    orc, ref = Oracle(46, 54, 368, 432, 17), Reference(46, 54, 368, 432, 17)
+    for seed, people, kw in [(900, 4, {}), (901, 33, {}), (902, 36, {"drop_limbs": (12,)}), (903, 6, {"noise": 1e-3})]:
+        conf, paf = synth.render_frame(seed, people, **kw)
+        o = orc.run(conf, paf)
+        assert helpers.humans_equal(o["humans"], ref.run(conf, paf)) is None, seed
