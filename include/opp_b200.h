@@ -155,8 +155,10 @@ int opp_resize_pair_device(opp_handle_t h, const float *conf, const float *paf, 
                            void *stream);
 
 /* Peak finding alone (smooth + NMS + raster-order peak list) on device feature maps, on the caller's
- * stream, writing the slot-0 scratch buffers: lets the bench time the kernel with its own events. */
-int opp_peaks_device(opp_handle_t h, const float *conf, int n_frames, void *stream);
+ * stream, writing the slot-0 scratch buffers: lets the bench time the kernel with its own events.
+ * With conf_up/paf_up (and paf) non-NULL it runs the variant that also materialises the up-sampled
+ * maps from inside the kernel, as opp_process does when both outputs are requested channels-first. */
+int opp_peaks_device(opp_handle_t h, const float *conf, const float *paf, int n_frames, float *conf_up, float *paf_up, void *stream);
 
 /* Device-side stopwatch over ALL slot streams: opp_timer_start records an event after everything
  * already enqueued; opp_timer_stop joins every slot stream, records, waits, and returns the elapsed

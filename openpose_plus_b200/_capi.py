@@ -74,7 +74,7 @@ def lib():
         L.opp_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.opp_resize_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.opp_resize_pair_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
-        L.opp_peaks_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.opp_peaks_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.opp_timer_start.argtypes = [C.c_void_p]
         L.opp_timer_stop.argtypes = [C.c_void_p]
         L.opp_timer_stop.restype = C.c_float

@@ -3,6 +3,7 @@
 // paf_processor_impl::operator() (/root/reference src/paf.cpp:38-57).
 #include <cmath>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,6 +32,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr; // materialising resize runs beside peak finding / grouping
     cudaEvent_t ev_start = nullptr, ev_done = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t tr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // OPP_TRACE: k1 start/end, k2 start/end, k3 end, copies end
     // device arena
     float *d_conf = nullptr, *d_paf = nullptr; // staged feature maps [B,19,h,w] / [B,38,h,w]
     float *d_hwc = nullptr;                    // staging for channels-last input
@@ -79,6 +81,10 @@ struct opp_handle_s {
     int force_tw = 0, force_th = 0;
     cudaStream_t timer_stream = nullptr;
     cudaEvent_t timer_t0 = nullptr, timer_t1 = nullptr;
+    bool trace = false;
+    bool fuse_resize = true;
+    bool k2_skip = true;
+    cudaEvent_t trace_base = nullptr;
 };
 
 #define CU(call)                                                                                      \
@@ -184,12 +190,19 @@ int alloc_slot(opp_handle_s *h, Slot &s)
     const opp_config_t &c = h->cfg;
     const size_t B = c.max_batch, hw = (size_t)c.feat_h * c.feat_w;
     const int capP = c.max_peaks_per_part, capC = c.max_cands_per_limb, capH = c.max_humans;
-    CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
+    // The store-bound resize runs on the low-priority side stream: its tens of thousands of short CTAs
+    // would otherwise occupy every SM ahead of the compute-bound peak / limb kernels it overlaps with.
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    if (getenv("OPP_NO_PRIORITY")) prio_hi = prio_lo;
+    CU(cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prio_hi));
+    CU(cudaStreamCreateWithPriority(&s.side, cudaStreamNonBlocking, prio_lo));
     CU(cudaEventCreate(&s.ev_start));
     CU(cudaEventCreate(&s.ev_done));
     CU(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
+    if (h->trace)
+        for (auto &e : s.tr) CU(cudaEventCreate(&e));
     CU(cudaMalloc(&s.d_conf, B * OPP_N_HEAT * hw * sizeof(float)));
     CU(cudaMalloc(&s.d_paf, B * OPP_N_PAF * hw * sizeof(float)));
     CU(cudaMalloc(&s.d_counters, h->counters_ints * sizeof(int)));
@@ -218,18 +231,24 @@ int *cnt_k3(opp_handle_s *h, Slot &s) { return cnt_k2(h, s) + h->cfg.max_batch; 
 int *cnt_stats(opp_handle_s *h, Slot &s) { return cnt_k3(h, s) + h->cfg.max_batch; }
 int *cnt_flags(opp_handle_s *h, Slot &s) { return cnt_stats(h, s) + (size_t)h->cfg.max_batch * 4; }
 
-void choose_k2_tiles(opp_handle_s *h, int n_frames, int &tw, int &th)
+void choose_k2_tiles(opp_handle_s *h, int n_frames, bool store, int &tw, int &th)
 {
     const OppGeom &g = h->g;
-    // column strips of at most 8 warps x 62 decided columns
+    // column strips of at most 7 warps x 62 decided columns (K2_FAST_MAX_THREADS = 224)
     const int S = g.S > 0 ? g.S : 1;
-    int nxs = (g.W + 62 * 8 - 1) / (62 * 8);
+    int nxs = (g.W + 62 * 7 - 1) / (62 * 7);
     if (nxs < 1) nxs = 1;
     tw = (g.w + nxs - 1) / nxs;
     th = g.h;
     (void)S;
-    // two resident CTAs per SM need each to stay under ~110 KB
-    while (k2_fast_smem_bytes(g, tw, th) > (size_t)110 * 1024 && th > 4) th = (th + 1) / 2;
+    // three resident CTAs per SM (the kernel is compiled for that): each must stay under ~72 KB, and
+    // row tiles of about 16 feature rows keep the last wave short
+    // (measured at 368x432: ~12 rows when the kernel also streams the up-sampled maps - short tiles
+    // keep the store flow even - and ~23 rows in skeleton-only mode, where per-CTA fixed costs dominate)
+    const int target = store ? 12 : 23;
+    int nys = (g.h + target - 1) / target;
+    th = (g.h + nys - 1) / nys;
+    while ((k2_fast_smem_bytes(g, tw, th) > (size_t)72 * 1024 || th > 60) && th > 4) th = (th + 1) / 2;
     // small batches: split rows too until the grid covers the chip about twice
     const long want = 2L * h->sm_count;
     while ((long)n_frames * OPP_N_PARTS * ((g.w + tw - 1) / tw) * ((g.h + th - 1) / th) < want && th > 6) th = (th + 1) / 2;
@@ -367,7 +386,14 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
             return OPP_ERR_INVALID;
         }
         h->counters_ints = (size_t)c.max_batch * (OPP_N_PARTS + 1 + 1 + 4 + 1);
+        h->trace = getenv("OPP_TRACE") != nullptr;
+        h->fuse_resize = getenv("OPP_NO_FUSE") == nullptr;
+        h->k2_skip = getenv("OPP_K2_NOSKIP") == nullptr;
         CU(cudaStreamCreateWithFlags(&h->timer_stream, cudaStreamNonBlocking));
+        if (h->trace) {
+            CU(cudaEventCreate(&h->trace_base));
+            CU(cudaEventRecord(h->trace_base, h->timer_stream));
+        }
         CU(cudaEventCreate(&h->timer_t0));
         CU(cudaEventCreate(&h->timer_t1));
         h->slots.resize(c.n_slots);
@@ -387,7 +413,7 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
     return OPP_OK;
 }
 
-static int fill_k2(opp_handle_s *h, Slot &s, const float *conf, const float *conf_up, int n, K2Params &k2);
+static int fill_k2(opp_handle_s *h, Slot &s, const float *conf, const float *conf_up, int n, bool store, K2Params &k2);
 
 static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
 {
@@ -451,11 +477,15 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
             conf_up_for_k2 = s.d_conf_up;
         }
     }
-    if (want_up) {
+    // Integer-scale fast path with both tensors requested channels-first: the peak kernel writes them itself.
+    const bool fuse_up = h->fast_k2 && h->fuse_resize && b.conf_up && b.paf_up && b.up_layout == OPP_LAYOUT_CHW &&
+                         (((uintptr_t)b.conf_up | (uintptr_t)b.paf_up) & 15) == 0 && (g.W & 3) == 0;
+    if (want_up && !fuse_up) {
         CU(cudaEventRecord(s.ev_fork, st));
         CU(cudaStreamWaitEvent(s.side, s.ev_fork, 0));
         forked = true;
         const bool conf_pending = b.conf_up && !(generic_needs_conf_up && b.up_layout == OPP_LAYOUT_CHW);
+        if (h->trace) CU(cudaEventRecord(s.tr[0], s.side));
         if (conf_pending && b.paf_up) { // both tensors in one launch
             K1Params k1{};
             k1.g = g, k1.n = n, k1.layout = b.up_layout;
@@ -475,9 +505,12 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
         }
     }
 
+    if (forked && h->trace) CU(cudaEventRecord(s.tr[1], s.side));
     // ---- peaks
+    if (h->trace) CU(cudaEventRecord(s.tr[2], st));
     K2Params k2{};
-    fill_k2(h, s, conf, conf_up_for_k2, n, k2);
+    fill_k2(h, s, conf, conf_up_for_k2, n, fuse_up, k2);
+    if (fuse_up) k2.paf = paf, k2.up_conf = b.conf_up, k2.up_paf = b.paf_up;
     int *d_flags = cnt_flags(h, s);
     if (h->fast_k2) {
         CU(launch_k2_fast(k2, n, st));
@@ -486,6 +519,7 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     }
     h->launches += 1;
 
+    if (h->trace) CU(cudaEventRecord(s.tr[3], st));
     // ---- limbs, matching, assembly
     K3Params k3 = h->k3_plan;
     k3.g = g, k3.paf = paf, k3.peaks = s.d_peaks, k3.part_ofs = s.d_part_ofs;
@@ -501,6 +535,7 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     CU(launch_k3(k3, n, h->k3_smem, st));
     h->launches += 1;
 
+    if (h->trace) CU(cudaEventRecord(s.tr[4], st));
     // ---- results
     if (dev_out) {
         if (b.frame_flags) CU(cudaMemcpyAsync(b.frame_flags, d_flags, n * sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -509,6 +544,7 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
         CU(cudaMemcpyAsync(s.h_flags, d_flags, n * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(s.h_humans, s.d_humans, (size_t)n * c.max_humans * sizeof(opp_human_t), cudaMemcpyDeviceToHost, st));
     }
+    if (h->trace) CU(cudaEventRecord(s.tr[5], st));
     if (forked) {
         CU(cudaEventRecord(s.ev_join, s.side));
         CU(cudaStreamWaitEvent(st, s.ev_join, 0));
@@ -575,6 +611,16 @@ int opp_wait(opp_handle_t h, int ticket)
         return OPP_ERR_CUDA;
     }
     cudaEventElapsedTime(&s.last_ms, s.ev_start, s.ev_done);
+    if (h->trace) {
+        float t[8] = {0};
+        cudaEventElapsedTime(&t[6], h->trace_base, s.ev_start);
+        cudaEventElapsedTime(&t[7], h->trace_base, s.ev_done);
+        const bool up = s.batch.conf_up || s.batch.paf_up;
+        for (int i = 0; i < 6; ++i)
+            if (i >= 2 || up) cudaEventElapsedTime(&t[i], h->trace_base, s.tr[i]);
+        fprintf(stderr, "[opp trace] ticket %d n=%d start %.3f | k1 %.3f-%.3f | k2 %.3f-%.3f | k3 -%.3f | copies -%.3f | done %.3f (ms)\n", s.ticket,
+                s.n_frames, t[6], t[0], t[1], t[2], t[3], t[4], t[5], t[7]);
+    }
     const opp_batch_t &b = s.batch;
     if (b.out_mem == OPP_MEM_HOST) {
         const int capH = h->cfg.max_humans;
@@ -657,7 +703,7 @@ int opp_resize_device(opp_handle_t h, const float *src, int channels, int n_fram
     return OPP_OK;
 }
 
-static int fill_k2(opp_handle_s *h, Slot &s, const float *conf, const float *conf_up, int n, K2Params &k2)
+static int fill_k2(opp_handle_s *h, Slot &s, const float *conf, const float *conf_up, int n, bool store, K2Params &k2)
 {
     const opp_config_t &c = h->cfg;
     k2.g = h->g, k2.conf = conf, k2.conf_up = conf_up;
@@ -667,8 +713,9 @@ static int fill_k2(opp_handle_s *h, Slot &s, const float *conf, const float *con
     k2.flags = cnt_flags(h, s);
     std::memcpy(k2.taps, h->taps, sizeof k2.taps);
     k2.thresh = 0.05f; // THRESH_HEAT, src/paf.cpp:60
+    k2.skip_thresh = h->k2_skip ? k2.thresh * (1.f - 1.f / 8192.f) : -INFINITY;
     if (h->fast_k2) {
-        choose_k2_tiles(h, n, k2.tw, k2.th);
+        choose_k2_tiles(h, n, store, k2.tw, k2.th);
         k2.nxs = (h->g.w + k2.tw - 1) / k2.tw, k2.nys = (h->g.h + k2.th - 1) / k2.th;
     }
     return OPP_OK;
@@ -688,20 +735,22 @@ int opp_resize_pair_device(opp_handle_t h, const float *conf, const float *paf, 
     return OPP_OK;
 }
 
-int opp_peaks_device(opp_handle_t h, const float *conf, int n_frames, void *stream)
+int opp_peaks_device(opp_handle_t h, const float *conf, const float *paf, int n_frames, float *conf_up, float *paf_up, void *stream)
 {
     if (!h || !conf || n_frames < 1 || n_frames > h->cfg.max_batch) return OPP_ERR_INVALID;
     if (!h->fast_k2) {
         set_err(&h->err, "opp_peaks_device: only the integer-scale peak kernel runs stand-alone");
         return OPP_ERR_INVALID;
     }
+    if ((conf_up || paf_up) && !(conf_up && paf_up && paf)) return OPP_ERR_INVALID;
     CU(cudaSetDevice(h->device));
     Slot &s = h->slots[0];
     if (s.busy) return OPP_ERR_BUSY;
     cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
     CU(cudaMemsetAsync(s.d_counters, 0, h->counters_ints * sizeof(int), st));
     K2Params k2{};
-    fill_k2(h, s, conf, nullptr, n_frames, k2);
+    fill_k2(h, s, conf, nullptr, n_frames, conf_up != nullptr, k2);
+    if (conf_up) k2.paf = paf, k2.up_conf = conf_up, k2.up_paf = paf_up;
     CU(launch_k2_fast(k2, n_frames, st));
     h->launches += 1;
     return OPP_OK;

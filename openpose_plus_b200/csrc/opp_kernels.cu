@@ -15,6 +15,8 @@
 
 #include <math_constants.h>
 
+#include <cstdlib>
+
 namespace
 {
 // include/openpose-plus/coco.h:11-53
@@ -86,6 +88,103 @@ __global__ void __launch_bounds__(OPP_THREADS) k1_replicate_chw(const K1Params p
             __stcs(drow + v, make_float4(s, s, s, s));
         }
     }
+}
+
+// Lean per-thread stores: one CTA per (channel, frame) plane; thread = (float4 column v, half of the S
+// replicated rows).  Per feature row a thread loads one value and issues S/2 16-byte streaming stores
+// through pre-computed row pointers: ~3.5 instructions per 512-byte warp store.
+template <int S>
+__global__ void __launch_bounds__(224) k1_replicate_rows(const K1Params p, int G, int n_items)
+{
+    // Persistent: a fixed, small number of CTAs per SM (chosen by the launcher) walks over the
+    // (row group, channel, frame) items, so the store stream keeps a bounded footprint and the
+    // compute-bound kernels it overlaps with always find room on every SM.
+    const int w = p.g.w, W = p.g.W, h = p.g.h, H = p.g.H;
+    const int W4 = W >> 2;
+    const int groups = (h + G - 1) / G;
+    const int Ctot = p.C + p.C2;
+    constexpr int HALF = S / 2;
+    const int t = threadIdx.x;
+    if (t >= 2 * W4) return;
+    const int half = t / W4, v = t - half * W4;
+    const int sofs = (v * 4) / S;
+    const size_t dofs = (size_t)(half * HALF) * W4 + v;
+    const size_t step = (size_t)S * W4;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int gi = item % groups;
+        const int t2 = item / groups;
+        int c = t2 % Ctot, C = p.C;
+        const int f = t2 / Ctot;
+        const float *src_base = p.src;
+        float *dst_base = p.dst;
+        if (c >= p.C) c -= p.C, C = p.C2, src_base = p.src2, dst_base = p.dst2;
+        const int i0 = gi * G, i1 = min(i0 + G, h);
+        const float *sp = src_base + ((size_t)f * C + c) * h * w + (size_t)i0 * w + sofs;
+        float4 *dp = reinterpret_cast<float4 *>(dst_base + ((size_t)f * C + c) * H * W) + (size_t)i0 * S * W4 + dofs;
+#pragma unroll 4
+        for (int i = i0; i < i1; ++i) {
+            const float sv = __ldg(sp);
+            sp += w;
+            const float4 val = make_float4(sv, sv, sv, sv);
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) __stcs(dp + (size_t)j * W4, val);
+            dp += step;
+        }
+    }
+}
+
+// TMA bulk-store variant (the default): a CTA expands G feature rows into shared memory once
+// (16-byte shared stores), then ONE thread hands each expanded row to the copy engine S times
+// (cp.async.bulk shared -> global, one per replicated output row).  The SM issues ~7 instructions per
+// KB written instead of ~90 with per-thread stores, so the store stream leaves the issue slots to the
+// compute-bound peak / limb kernels it runs beside.  Two shared buffers: the rows of item k+1 are
+// expanded while the copy engine still drains item k.
+__device__ __forceinline__ void bulk_store_row(float *gdst, const float *ssrc, unsigned bytes)
+{
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+}
+
+template <int S>
+__global__ void __launch_bounds__(128) k1_replicate_bulk(const K1Params p, int G, int n_items)
+{
+    extern __shared__ __align__(128) float sbuf[]; // [2][G][W]
+    const int w = p.g.w, W = p.g.W, h = p.g.h, H = p.g.H;
+    const int groups = (h + G - 1) / G;
+    const int Ctot = p.C + p.C2;
+    const int W4 = W >> 2;
+    int buf = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, buf ^= 1) {
+        const int gi = item % groups;
+        const int t2 = item / groups;
+        int c = t2 % Ctot, C = p.C;
+        const int f = t2 / Ctot;
+        const float *src_base = p.src;
+        float *dst_base = p.dst;
+        if (c >= p.C) c -= p.C, C = p.C2, src_base = p.src2, dst_base = p.dst2;
+        const int i0 = gi * G, i1 = min(i0 + G, h);
+        const float *src = src_base + ((size_t)f * C + c) * h * w + (size_t)i0 * w;
+        float *dst = dst_base + ((size_t)f * C + c) * H * W;
+        float *sb = sbuf + (size_t)buf * G * W;
+        // the copies issued from this buffer two items ago must have finished READING it (bulk groups
+        // are per thread: every issuing thread waits on its own)
+        const bool issuer = threadIdx.x < G * S;
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
+        for (int t = threadIdx.x; t < (i1 - i0) * W4; t += blockDim.x) {
+            const int r = t / W4, v = t - r * W4;
+            const float sv = __ldg(src + r * w + (v * 4) / S);
+            reinterpret_cast<float4 *>(sb)[r * W4 + v] = make_float4(sv, sv, sv, sv);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the copy engine
+        __syncthreads();
+        if (issuer) {
+            const int r = threadIdx.x / S, q = threadIdx.x - r * S;
+            if (r < i1 - i0) bulk_store_row(dst + ((size_t)(i0 + r) * S + q) * W, sb + (size_t)r * W, (unsigned)(W * sizeof(float)));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (threadIdx.x < G * S) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory must outlive the reads
 }
 
 // Any geometry / layout: one thread per output element, table-driven 2x2-tap sample.
@@ -173,12 +272,15 @@ __device__ void finalize_frame_peaks(const K2Params &p, int frame, int *s_keys /
 
 __device__ __forceinline__ bool tile_done_is_last(int *counter, int total)
 {
+    // Every CTA publishes its writes with a release-increment (ordered after the whole CTA's writes by
+    // the barrier); only the CTA that sees the final count pays for the acquire side (L1 invalidate).
     __shared__ int s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = (atomicAdd(counter, 1) == total - 1);
-        __threadfence();
+        int old;
+        asm volatile("atom.add.release.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+        s_last = (old == total - 1);
+        if (s_last) __threadfence();
     }
     __syncthreads();
     return s_last != 0;
@@ -249,17 +351,31 @@ __device__ __forceinline__ void col_all(const float *__restrict__ k, float a, fl
     for (int ph = 0; ph < S; ++ph) s[ph] = col_phase<S, R>(k, ph, a, b, c, a_sp, c_sp);
 }
 
+#ifndef K2_FAST_MAX_THREADS
+#define K2_FAST_MAX_WARPS 7       // column groups per CTA: 7 x 62 decided columns >= 432
+#define K2_FAST_MAX_THREADS 224
+#define K2_FAST_MIN_CTAS 3
+#endif
+
 // State of the running 3x3 max for one image column: horizontal 3-max of the two previous rows and
 // the smoothed value of the previous row (the one being decided).
 struct NmsState {
     float pp_h, p_h, p_s;
 };
 
-template <int S, int R>
-__global__ void __launch_bounds__(OPP_THREADS, 2) k2_peaks_fast(const K2Params p)
+// STORE = true additionally materialises the up-sampled maps from inside this kernel (the resize of
+// src/post-process.h:24-49 fused with its consumer): grid.y grows to 19 and the CTA of "part" k
+// streams heat map k and PAF channels 2k, 2k+1 of its tile to HBM, 12 16-byte stores per thread and
+// feature row, interleaved with the filter arithmetic of the same rows.  The store stream then shares
+// SMs with the FP32 work by construction instead of relying on two kernels being co-scheduled (a
+// stand-alone resize next to this kernel serialises: both want every SM).  CTA 18 (background heat
+// map, PAF 36/37) only stores.
+template <int S, int R, bool STORE>
+__global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peaks_fast(const K2Params p)
 {
     extern __shared__ __align__(16) float smem[];
     const int frame = blockIdx.z, part = blockIdx.y;
+    const bool compute = part < OPP_N_PARTS;
     const int tx = blockIdx.x % p.nxs, ty = blockIdx.x / p.nxs;
     const int h = p.g.h, w = p.g.w, H = S * h;
     const int ja = tx * p.tw, jb = min(ja + p.tw, w);
@@ -270,41 +386,165 @@ __global__ void __launch_bounds__(OPP_THREADS, 2) k2_peaks_fast(const K2Params p
     const int RW = S * ncol;
     float *L = smem;                          // [nr][w] feature rows
     float *Rrow = smem + ((nr * w + 3) & ~3); // [nr][RW] row-pass result
+    float *Pf = Rrow + ((nr * RW + 3) & ~3);  // [2][ib-ia][w] PAF feature rows of the tile (STORE only)
     const float *src = p.conf + ((size_t)frame * OPP_N_HEAT + part) * h * w + ilo * w;
     for (int t = threadIdx.x; t < nr * w; t += blockDim.x) L[t] = __ldg(src + t);
+    if (STORE) {
+        // staged up front: a load issued next to the store stream would queue behind it for microseconds
+        const int nt = (ib - ia) * w;
+        const float *ps = p.paf + (((size_t)frame * OPP_N_PAF + 2 * part) * h + ia) * w;
+        for (int t = threadIdx.x; t < nt; t += blockDim.x) Pf[t] = __ldg(ps + t), Pf[nt + t] = __ldg(ps + (size_t)h * w + t);
+    }
     __syncthreads();
 
+    // ---- which blocks can hold a peak at all?  A pixel of feature cell (r, c) is filtered from the 3x3
+    // cells around it (R <= S, reflection included).  Every float operation of the filter is monotone
+    // in its inputs and the taps are positive, so if those nine values are all <= t then the smoothed
+    // pixel is <= t * (sum of taps, rounded up) < t * (1 + 2^-17).  With t = thresh * (1 - 2^-13) the
+    // pixel cannot exceed thresh, cannot be a peak, and cannot outrank a pixel that is one: its block
+    // (column group x feature row) need not be computed and its pixels may stand as -inf for their
+    // neighbours.  Exact for every input; dense maps simply have every block active.
+    __shared__ unsigned long long s_act[64], s_need[64], s_blk[K2_FAST_MAX_WARPS];
+    const int X0 = S * ja, X1 = S * jb;
+    const int ngroups = (X1 - X0 + 61) / 62;
+    if (compute) {
+        const float t_skip = p.skip_thresh;
+        const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5, nwarps_ = blockDim.x >> 5;
+        // (1) cells above the skip threshold, one ballot per 32 cells (a warp per feature row) ...
+        for (int r = warp_; r < nr; r += nwarps_) {
+            unsigned long long bits = 0ull;
+            for (int c0 = 0; c0 < ncol; c0 += 32) {
+                const bool hot = c0 + lane_ < ncol && L[r * w + jlo + c0 + lane_] > t_skip;
+                bits |= (unsigned long long)__ballot_sync(0xffffffffu, hot) << c0;
+            }
+            // only decided cells [ja, jb) are ever tested, and their 3x3 neighbourhoods lie inside the
+            // staged cells [jlo, jhi) and the staged rows (or end at the image border)
+            if (lane_ == 0) s_act[r] = bits;
+        }
+        __syncthreads();
+        // ... dilated 3x3 on the bit rows (lane = feature row)
+        if (warp_ == 0) {
+            unsigned long long d[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int r = lane_ + 32 * k;
+                unsigned long long v = 0ull;
+                if (r < nr) {
+                    v = s_act[r];
+                    if (r > 0) v |= s_act[r - 1];
+                    if (r + 1 < nr) v |= s_act[r + 1];
+                    v |= (v << 1) | (v >> 1);
+                }
+                d[k] = v;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if (lane_ + 32 * k < nr) s_act[lane_ + 32 * k] = d[k];
+        }
+        __syncthreads();
+        // (2) active blocks per column group (one warp; lane = feature row) and (3) the cells the row pass must produce
+        if (warp_ == 0) {
+            unsigned long long dec[K2_FAST_MAX_WARPS], span[K2_FAST_MAX_WARPS];
+#pragma unroll
+            for (int g = 0; g < K2_FAST_MAX_WARPS; ++g) {
+                const int xa = X0 + 62 * g, xb = min(xa + 62, X1) - 1;
+                const int ca = xa / S - jlo, cb = xb / S - jlo;
+                const int sa = max(xa - 1, S * jlo) / S - jlo, sb = min(xb + 1, S * jhi - 1) / S - jlo;
+                dec[g] = g < ngroups ? ((cb - ca >= 63 ? ~0ull : ((1ull << (cb - ca + 1)) - 1)) << ca) : 0ull;
+                span[g] = g < ngroups ? ((sb - sa >= 63 ? ~0ull : ((1ull << (sb - sa + 1)) - 1)) << sa) : 0ull;
+            }
+            unsigned long long blk[K2_FAST_MAX_WARPS];
+#pragma unroll
+            for (int g = 0; g < K2_FAST_MAX_WARPS; ++g) {
+                const unsigned lo = __ballot_sync(0xffffffffu, lane_ < nr && (s_act[lane_] & dec[g]) != 0);
+                const unsigned hi = __ballot_sync(0xffffffffu, lane_ + 32 < nr && (s_act[min(lane_ + 32, 63)] & dec[g]) != 0);
+                blk[g] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+                if (lane_ == 0) s_blk[g] = blk[g];
+            }
+            for (int r = lane_; r < nr; r += 32) {
+                unsigned long long need = 0ull;
+                const unsigned long long near3 = (r > 0 ? 7ull << (r - 1) : 3ull); // rows r-1, r, r+1
+#pragma unroll
+                for (int g = 0; g < K2_FAST_MAX_WARPS; ++g)
+                    if (blk[g] & near3) need |= span[g];
+                s_need[r] = need;
+            }
+        }
+        __syncthreads();
+    }
+
     // ---- row pass: one thread per (feature row, feature column) -> S outputs
-    for (int it = threadIdx.x; it < nr * ncol; it += blockDim.x) {
-        const int r = it / ncol, c = jlo + (it - r * ncol);
-        const float *Lr = L + r * w;
-        const float b = Lr[c];
-        const float a_raw = Lr[max(c - 1, 0)], c_raw = Lr[min(c + 1, w - 1)];
-        const float a = c > 0 ? a_raw : b, cc = c < w - 1 ? c_raw : b;
-        const float a_sp = c > 0 ? a_raw : c_raw, c_sp = c < w - 1 ? c_raw : a_raw;
-        float out[S];
-        row_taps<S, R>(p.taps, a, b, cc, a_sp, c_sp, out);
-        float *d = Rrow + r * RW + S * (c - jlo);
-        if (S % 4 == 0) {
+    if (compute) {
+        for (int it = threadIdx.x; it < nr * ncol; it += blockDim.x) {
+            const int r = it / ncol, c = jlo + (it - r * ncol);
+            if (!((s_need[r] >> (c - jlo)) & 1ull)) continue; // no active block reads this cell
+            const float *Lr = L + r * w;
+            const float b = Lr[c];
+            const float a_raw = Lr[max(c - 1, 0)], c_raw = Lr[min(c + 1, w - 1)];
+            const float a = c > 0 ? a_raw : b, cc = c < w - 1 ? c_raw : b;
+            const float a_sp = c > 0 ? a_raw : c_raw, c_sp = c < w - 1 ? c_raw : a_raw;
+            float out[S];
+            row_taps<S, R>(p.taps, a, b, cc, a_sp, c_sp, out);
+            float *d = Rrow + r * RW + S * (c - jlo);
+            if (S % 4 == 0) {
 #pragma unroll
-            for (int q = 0; q < S; q += 4) *reinterpret_cast<float4 *>(d + q) = make_float4(out[q], out[q + 1], out[q + 2], out[q + 3]);
-        } else {
+                for (int q = 0; q < S; q += 4) *reinterpret_cast<float4 *>(d + q) = make_float4(out[q], out[q + 1], out[q + 2], out[q + 3]);
+            } else {
 #pragma unroll
-            for (int q = 0; q < S; ++q) d[q] = out[q];
+                for (int q = 0; q < S; ++q) d[q] = out[q];
+            }
         }
     }
     __syncthreads();
 
-    // ---- column pass + 3x3 max + threshold.  A warp walks down 64 image columns, two per lane: lane l
-    // holds columns xg0-1+2l and xg0+2l, so 62 columns are decided per warp and the outermost two only
-    // feed their neighbours.  Columns that do not exist read -inf, which the filter maps to -inf.
-    const int X0 = S * ja, X1 = S * jb, Y0 = S * ia;
     const int xlo = S * jlo, xhi = S * jhi; // columns present in Rrow
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int ngroups = (X1 - X0 + 61) / 62;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float NINF = -CUDART_INF_F;
-    for (int g = warp; g < ngroups; g += nwarps) {
-        const int x0 = X0 + 62 * g - 1 + 2 * lane, x1 = x0 + 1;
+
+    // ---- store plan (STORE): thread = (16-byte column v of the tile, half of the S replicated rows);
+    // per feature row it writes HALF rows of its column in each of the three planes, interleaved
+    // with the filter arithmetic of the same feature row.
+    constexpr int HALF = S / 2;
+    const int W4 = (S * w) >> 2, Wt4 = (X1 - X0) >> 2;
+    const bool st_on = STORE && (int)threadIdx.x < 2 * Wt4;
+    // Store order: plane after plane (heat tile, then the two PAF tiles), three feature rows per
+    // iteration of the column loop, so each CTA writes ONE contiguous stream at a time (DRAM pages).
+    const int nrt = ib - ia;
+    float4 *ob_h = nullptr, *ob_p = nullptr;
+    int fcol = 0;
+    const size_t plane4 = (size_t)H * W4;
+    if (st_on) {
+        const int half = (int)threadIdx.x / Wt4, v = (int)threadIdx.x - half * Wt4;
+        fcol = ja + (4 * v) / S;
+        const size_t tofs = (size_t)(S * ia + half * HALF) * W4 + (X0 >> 2) + v;
+        ob_h = reinterpret_cast<float4 *>(p.up_conf) + ((size_t)frame * OPP_N_HEAT + part) * plane4 + tofs;
+        ob_p = reinterpret_cast<float4 *>(p.up_paf) + ((size_t)frame * OPP_N_PAF + 2 * part) * plane4 + tofs;
+    }
+    int st_unit = 0;
+    auto store_rows = [&]() {
+        if (st_on) {
+#pragma unroll
+            for (int rep = 0; rep < 3; ++rep, ++st_unit) {
+                const int plane = st_unit / nrt, r = st_unit - plane * nrt;
+                const float sv = plane == 0 ? L[(ia - ilo + r) * w + fcol] : Pf[((plane - 1) * nrt + r) * w + fcol];
+                float4 *o = (plane == 0 ? ob_h : ob_p + (size_t)(plane - 1) * plane4) + (size_t)r * S * W4;
+                const float4 val = make_float4(sv, sv, sv, sv);
+#pragma unroll
+                for (int j = 0; j < HALF; ++j) __stcs(o + (size_t)j * W4, val);
+            }
+        }
+    };
+
+    if (!compute || warp >= ngroups) { // store-only CTA (background) or a warp without a column group
+        if (STORE)
+            for (int i = ia; i < ib; ++i) store_rows();
+        if (!compute) return;
+    } else {
+        // ---- column pass + 3x3 max + threshold.  A warp walks down 64 image columns, two per lane: lane l
+        // holds columns xg0-1+2l and xg0+2l, so 62 columns are decided per warp and the outermost two only
+        // feed their neighbours.  Columns that do not exist read -inf, which the filter maps to -inf.
+        const int x0 = X0 + 62 * warp - 1 + 2 * lane, x1 = x0 + 1;
         const bool have0 = x0 >= xlo && x0 < xhi, have1 = x1 >= xlo && x1 < xhi;
         const float thr0 = (lane >= 1 && x0 < X1) ? p.thresh : CUDART_INF_F;
         const float thr1 = (lane <= 30 && x1 < X1) ? p.thresh : CUDART_INF_F;
@@ -344,26 +584,45 @@ __global__ void __launch_bounds__(OPP_THREADS, 2) k2_peaks_fast(const K2Params p
         if (i_first > 0) a0 = ld0(i_first - 1), a1 = ld1(i_first - 1);
         b0 = ld0(i_first), b1 = ld1(i_first);
         float s0[S], s1[S];
+        const unsigned long long blk = s_blk[warp]; // bit r: block (this column group, feature row ilo + r) is active
+        // the mask is the same in every lane; the vote makes that visible to the compiler (uniform branch,
+        // so the shuffles below stay in convergent code)
+        auto active = [&](int i) { return __any_sync(0xffffffffu, ((blk >> (i - ilo)) & 1ull) != 0) != 0; };
+        bool open = false; // the last computed image row still waits for its decision
+        auto close_block = [&](int y_next) { // the rows below are provably <= thresh: they count as -inf
+            step(NINF, NINF, 0, true);
+            flush(y_next);
+            n0.pp_h = n0.p_h = n0.p_s = NINF, n1.pp_h = n1.p_h = n1.p_s = NINF;
+            open = false;
+        };
         if (ia > 0) { // halo row above the tile: only its last image row is needed
             const int i = ia - 1;
             c0 = ld0(i + 1), c1 = ld1(i + 1); // i + 1 = ia <= h - 1
-            col_all<S, R>(p.taps, i > 0 ? a0 : b0, b0, c0, i > 0 ? a0 : c0, c0, s0);
-            col_all<S, R>(p.taps, i > 0 ? a1 : b1, b1, c1, i > 0 ? a1 : c1, c1, s1);
-            step(s0[S - 1], s1[S - 1], 0, false);
-            n0.p_s = NINF, n1.p_s = NINF; // that row belongs to the tile above
+            if (active(i)) {
+                col_all<S, R>(p.taps, i > 0 ? a0 : b0, b0, c0, i > 0 ? a0 : c0, c0, s0);
+                col_all<S, R>(p.taps, i > 0 ? a1 : b1, b1, c1, i > 0 ? a1 : c1, c1, s1);
+                step(s0[S - 1], s1[S - 1], 0, false);
+                n0.p_s = NINF, n1.p_s = NINF; // that row belongs to the tile above
+            }
             a0 = b0, b0 = c0, a1 = b1, b1 = c1;
         }
         for (int i = ia; i < ib; ++i) {
+            if (STORE) store_rows();
             const bool top = i == 0, bot = i == h - 1;
             c0 = bot ? 0.f : ld0(i + 1), c1 = bot ? 0.f : ld1(i + 1);
-            col_all<S, R>(p.taps, top ? b0 : a0, b0, bot ? b0 : c0, top ? c0 : a0, bot ? a0 : c0, s0);
-            col_all<S, R>(p.taps, top ? b1 : a1, b1, bot ? b1 : c1, top ? c1 : a1, bot ? a1 : c1, s1);
+            if (active(i)) {
+                col_all<S, R>(p.taps, top ? b0 : a0, b0, bot ? b0 : c0, top ? c0 : a0, bot ? a0 : c0, s0);
+                col_all<S, R>(p.taps, top ? b1 : a1, b1, bot ? b1 : c1, top ? c1 : a1, bot ? a1 : c1, s1);
 #pragma unroll
-            for (int ph = 0; ph < S; ++ph) step(s0[ph], s1[ph], ph, true);
-            flush(S * i);
+                for (int ph = 0; ph < S; ++ph) step(s0[ph], s1[ph], ph, true);
+                flush(S * i);
+                open = true;
+            } else if (open) {
+                close_block(S * i);
+            }
             a0 = b0, b0 = c0, a1 = b1, b1 = c1;
         }
-        if (ib < h) { // halo row below the tile: its first image row closes the last row of the tile
+        if (ib < h && active(ib)) { // halo row below the tile: its first image row closes the last row of the tile
             const int i = ib;
             const bool bot = i == h - 1;
             c0 = bot ? 0.f : ld0(i + 1), c1 = bot ? 0.f : ld1(i + 1);
@@ -371,11 +630,9 @@ __global__ void __launch_bounds__(OPP_THREADS, 2) k2_peaks_fast(const K2Params p
             col_all<S, R>(p.taps, a1, b1, bot ? b1 : c1, a1, bot ? a1 : c1, s1);
             step(s0[0], s1[0], 0, true);
             flush(S * i);
-        } else { // bottom image edge: the row below does not exist
-            step(NINF, NINF, 0, true);
-            flush(H);
+        } else if (open) { // bottom image edge, or an inactive block below: that row counts as -inf
+            close_block(S * ib);
         }
-        (void)Y0;
     }
 
     if (tile_done_is_last(p.cnt.k2_done + frame, p.nxs * p.nys * OPP_N_PARTS))
@@ -951,6 +1208,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const K3Params p)
 // launchers
 // ------------------------------------------------------------------------------------------------
 static int g_max_smem = 48 * 1024;
+static int g_sm_count = 148;
 
 // opt in to the large dynamic shared-memory carve-out (the per-block limit counts static shared memory too)
 template <typename Kern> static cudaError_t allow_big_smem(Kern kern, int *dyn_limit)
@@ -962,20 +1220,28 @@ template <typename Kern> static cudaError_t allow_big_smem(Kern kern, int *dyn_l
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, *dyn_limit);
 }
 
-template <int S, int R>
+template <int S, int R, bool STORE>
 static cudaError_t launch_k2_fast_t(const K2Params &p, int n_frames, size_t smem, cudaStream_t st)
 {
     static int dyn_limit = 0;
     if (!dyn_limit) {
-        cudaError_t e = allow_big_smem(k2_peaks_fast<S, R>, &dyn_limit);
+        cudaError_t e = allow_big_smem(k2_peaks_fast<S, R, STORE>, &dyn_limit);
         if (e != cudaSuccess) return e;
     }
     if (smem > (size_t)dyn_limit) return cudaErrorInvalidValue;
-    dim3 grid(p.nxs * p.nys, OPP_N_PARTS, n_frames);
+    dim3 grid(p.nxs * p.nys, STORE ? OPP_N_HEAT : OPP_N_PARTS, n_frames);
     const int groups = (S * p.tw + 61) / 62;
-    const int threads = 32 * (groups < 1 ? 1 : (groups > OPP_THREADS / 32 ? OPP_THREADS / 32 : groups));
-    k2_peaks_fast<S, R><<<grid, threads, smem, st>>>(p);
+    if (groups < 1 || groups > K2_FAST_MAX_WARPS || p.th + 4 > 64 || p.tw + 2 > 64) return cudaErrorInvalidValue; // 64-bit activity masks
+    const int threads = 32 * groups;
+    if (STORE && 4 * p.tw > threads) return cudaErrorInvalidValue; // two threads per 16-byte column of the tile
+    k2_peaks_fast<S, R, STORE><<<grid, threads, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+template <int S, int R>
+static cudaError_t launch_k2_fast_sr(const K2Params &p, int n_frames, size_t smem, cudaStream_t st)
+{
+    return p.up_conf ? launch_k2_fast_t<S, R, true>(p, n_frames, smem, st) : launch_k2_fast_t<S, R, false>(p, n_frames, smem, st);
 }
 
 bool k2_fast_supported(const OppGeom &g)
@@ -989,7 +1255,8 @@ size_t k2_fast_smem_bytes(const OppGeom &g, int tw, int th)
     const int nr = (th + 4 < g.h) ? th + 4 : g.h;
     const int ncol = (tw + 2 < g.w) ? tw + 2 : g.w;
     size_t fl = ((size_t)nr * g.w + 3) & ~(size_t)3;
-    fl += (size_t)nr * g.S * ncol;
+    fl += ((size_t)nr * g.S * ncol + 3) & ~(size_t)3;
+    fl += 2 * (size_t)(th < g.h ? th : g.h) * g.w; // PAF feature rows of the fused-store variant
     return fl * sizeof(float);
 }
 
@@ -1000,9 +1267,9 @@ cudaError_t launch_k2_fast(const K2Params &p, int n_frames, cudaStream_t st)
     if ((size_t)OPP_N_PARTS * p.capP * sizeof(int) > need) need = (size_t)OPP_N_PARTS * p.capP * sizeof(int);
     if (need > (size_t)g_max_smem) return cudaErrorInvalidValue;
     switch (p.g.K) {
-    case 17: return launch_k2_fast_t<8, 8>(p, n_frames, need, st);
-    case 13: return launch_k2_fast_t<8, 6>(p, n_frames, need, st);
-    case 9: return launch_k2_fast_t<8, 4>(p, n_frames, need, st);
+    case 17: return launch_k2_fast_sr<8, 8>(p, n_frames, need, st);
+    case 13: return launch_k2_fast_sr<8, 6>(p, n_frames, need, st);
+    case 9: return launch_k2_fast_sr<8, 4>(p, n_frames, need, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -1048,6 +1315,29 @@ static bool k1_fast_ok(const K1Params &p)
 cudaError_t launch_k1(const K1Params &p, cudaStream_t st)
 {
     const OppGeom &g = p.g;
+    static const int mode = getenv("OPP_K1_MODE") ? atoi(getenv("OPP_K1_MODE")) : 2; // 0 rows, 1 TMA bulk, 2 first version
+    if (k1_fast_ok(p) && mode == 0 && 2 * (g.W >> 2) <= 224) {
+        static const int G = getenv("OPP_K1_G") ? atoi(getenv("OPP_K1_G")) : 4; // feature rows per item: 32 output rows, 55 KB contiguous
+        static const int nc = getenv("OPP_K1_CTAS") ? atoi(getenv("OPP_K1_CTAS")) : 3;
+        const long n_items = (long)((g.h + G - 1) / G) * (p.C + p.C2) * p.n;
+        long grid = (long)g_sm_count * nc;
+        if (grid > n_items) grid = n_items;
+        k1_replicate_rows<8><<<(unsigned)grid, 224, 0, st>>>(p, G, (int)n_items);
+        return cudaGetLastError();
+    }
+    if (k1_fast_ok(p) && mode == 1) {
+        const int G = 8; // feature rows per item: 8 x 8 rows of W floats = 64 bulk copies, 2 x 13.8 KB shared at W = 432
+        const int groups = (g.h + G - 1) / G;
+        const long n_items = (long)groups * (p.C + p.C2) * p.n;
+        const size_t smem = 2 * (size_t)G * g.W * sizeof(float);
+        static int ctas_per_sm = getenv("OPP_K1_CTAS") ? atoi(getenv("OPP_K1_CTAS")) : 2;
+        long grid = (long)g_sm_count * ctas_per_sm;
+        if (grid > n_items) grid = n_items;
+        if (smem <= 48 * 1024) {
+            k1_replicate_bulk<8><<<(unsigned)grid, 128, smem, st>>>(p, G, (int)n_items);
+            return cudaGetLastError();
+        }
+    }
     if (k1_fast_ok(p)) {
         const int rows = 4; // source rows per CTA -> 32 output rows
         dim3 grid((g.h + rows - 1) / rows, p.C + p.C2, p.n);
@@ -1083,5 +1373,7 @@ cudaError_t launch_hwc_to_chw(const float *src, float *dst, int n, int C, int h,
 cudaError_t opp_kernels_init(int max_smem_optin)
 {
     g_max_smem = max_smem_optin;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) g_sm_count = sms;
     return cudaSuccess;
 }

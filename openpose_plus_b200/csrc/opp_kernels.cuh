@@ -34,7 +34,11 @@ struct OppCounters {
 struct K2Params {
     OppGeom g;
     const float *conf;    // [n,19,h,w] feature maps
-    const float *conf_up; // [n,19,H,W] materialised maps (generic kernel only)
+    const float *conf_up; // [n,19,H,W] materialised maps (INPUT of the generic kernel only)
+    // fused materialisation (fast kernel): when up_conf != nullptr the kernel also writes both up-sampled tensors
+    const float *paf;     // [n,38,h,w]
+    float *up_conf;       // [n,19,H,W]
+    float *up_paf;        // [n,38,H,W]
     int nxs, nys, tw, th; // tiling in feature-map units (fast kernel) / output tiles (generic)
     int capP;
     OppCounters cnt;
@@ -44,6 +48,7 @@ struct K2Params {
     int *flags;           // [n]
     float taps[OPP_MAX_KSIZE + 1];
     float thresh;
+    float skip_thresh; // blocks whose 3x3 feature neighbourhood stays <= this cannot hold a peak; -inf disables the skip
 };
 
 struct K3Params {

@@ -59,3 +59,25 @@ def test_generic_kernel_sizes_and_scales(mods):
                         (369, 433, 9), (46 * 3, 54 * 3, 7), (46 * 4, 54 * 4, 9), (368, 432 * 2, 17)]:
         eng, orc = Engine(46, 54, oh, ow, gauss_kernel_size=k, max_batch=2, max_peaks_per_part=512), Oracle(46, 54, oh, ow, k)
         H.run_and_check(eng, orc, conf, paf, "generic %dx%d k=%d" % (oh, ow, k))
+
+
+def test_values_around_the_peak_threshold(mods):
+    """The peak kernel skips blocks that provably stay below THRESH_HEAT; maps whose smoothed maxima sit
+    just below / just above 0.05, flat backgrounds near it, and isolated spikes must still be bit-exact."""
+    Engine, Oracle, H = mods
+    eng, orc = Engine(46, 54, max_batch=8, max_peaks_per_part=512, max_cands_per_limb=8192, max_humans=512), Oracle(46, 54, 368, 432, 17)
+    conf, paf = synth.render_batch(8, n_people=6, seed0=600)
+    rng = np.random.default_rng(9)
+    for f, target in enumerate([0.0499, 0.05, 0.0501, 0.0505, 0.051, 0.052, 0.055, 0.06]):
+        # scale so that the MEDIAN blob's smoothed maximum lands on `target`: about half the blobs pass the threshold
+        sm = orc.run(conf[f], paf[f], maps=True)["smoothed"][:18]
+        peaks = np.sort(sm.reshape(18, -1).max(axis=1))
+        conf[f, :18] *= np.float32(target / peaks[9])
+    H.run_and_check(eng, orc, conf, paf, "scaled")
+    conf2, paf2 = synth.render_batch(8, n_people=4, seed0=700)
+    # flat backgrounds just BELOW the threshold (a flat background above it makes every pixel a peak) + isolated spikes
+    for f, bg in enumerate([0.0499, 0.04999, 0.049999, 0.0495, 0.049, 0.045, 0.03, 0.0]):
+        conf2[f, :18] = np.maximum(conf2[f, :18], np.float32(bg))
+        ys, xs = rng.integers(0, 46, 12), rng.integers(0, 54, 12)
+        conf2[f, rng.integers(0, 18, 12), ys, xs] = rng.uniform(0.04, 0.9, 12).astype(np.float32)
+    H.run_and_check(eng, orc, conf2, paf2, "background")
