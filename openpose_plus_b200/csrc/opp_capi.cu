@@ -156,14 +156,17 @@ void plan_k3_smem(opp_handle_s *h)
     p.off_used = (int)off, off += align_up(2 * (size_t)capP, 16);
     p.off_misc = (int)off, off += 64;
     const size_t phase1 = off;
-    // assembly phase (re-uses the same bytes)
+    // assembly phase (re-uses the same bytes): partial humans, survivors, connections, peak x/y/score
     off = 0;
     p.off_href = 0, off += align_up((size_t)capH * 21 * sizeof(int), 16);
-    p.off_conn = (int)off, off += align_up((size_t)capP * sizeof(opp_conn_t), 16);
-    const size_t score_bytes = (size_t)OPP_N_PARTS * capP * sizeof(float);
-    p.score_in_smem = off + score_bytes <= budget / 2;
+    p.off_keep = (int)off, off += align_up((size_t)capH * sizeof(int), 16);
+    const size_t conn_all = (size_t)OPP_N_PAIRS * capP * sizeof(opp_conn_t), conn_one = (size_t)capP * sizeof(opp_conn_t);
+    const size_t pk_bytes = (size_t)OPP_N_PARTS * capP * 3 * sizeof(float);
+    p.conns_in_smem = off + conn_all + pk_bytes <= (size_t)(budget * 0.45);
+    p.off_conn = (int)off, off += align_up(p.conns_in_smem ? conn_all : conn_one, 16);
+    p.score_in_smem = off + pk_bytes <= budget / 2;
     p.off_score = (int)off;
-    if (p.score_in_smem) off += score_bytes;
+    if (p.score_in_smem) off += pk_bytes;
     h->k3_smem = phase1 > off ? phase1 : off;
 }
 

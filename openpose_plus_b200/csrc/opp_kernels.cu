@@ -15,6 +15,7 @@
 
 #include <math_constants.h>
 
+#include <cstdint>
 #include <cstdlib>
 
 namespace
@@ -33,6 +34,26 @@ __device__ __forceinline__ int reflect101(int p, int n)
 }
 
 __device__ __forceinline__ int clip_idx(int v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); }
+
+// Asynchronous global -> shared staging (cp.async / LDGSTS): every thread queues all its pieces
+// before anything waits, so a tile costs one memory round trip instead of one per loop iteration.
+// 16-byte pieces when both sides are 16-byte aligned, 4-byte pieces otherwise.  Completed by
+// stage_wait() followed by __syncthreads().
+__device__ __forceinline__ void stage_async(float *sdst, const float *gsrc, int n)
+{
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(sdst);
+    if (((reinterpret_cast<uintptr_t>(gsrc) | sbase) & 15) == 0) {
+        const int n4 = n >> 2;
+        for (int t = threadIdx.x; t < n4; t += blockDim.x)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * t), "l"(gsrc + 4 * t) : "memory");
+        for (int t = 4 * n4 + threadIdx.x; t < n; t += blockDim.x)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbase + 4u * t), "l"(gsrc + t) : "memory");
+    } else {
+        for (int t = threadIdx.x; t < n; t += blockDim.x)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbase + 4u * t), "l"(gsrc + t) : "memory");
+    }
+}
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // One sample of the area-mode up-sampled map (cv::resize INTER_AREA, dst >= src): horizontal 2-tap
 // on the two source rows, then vertical 2-tap.  Same float operations as the row-buffer form.
@@ -388,13 +409,15 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
     float *Rrow = smem + ((nr * w + 3) & ~3); // [nr][RW] row-pass result
     float *Pf = Rrow + ((nr * RW + 3) & ~3);  // [2][ib-ia][w] PAF feature rows of the tile (STORE only)
     const float *src = p.conf + ((size_t)frame * OPP_N_HEAT + part) * h * w + ilo * w;
-    for (int t = threadIdx.x; t < nr * w; t += blockDim.x) L[t] = __ldg(src + t);
+    stage_async(L, src, nr * w);
     if (STORE) {
         // staged up front: a load issued next to the store stream would queue behind it for microseconds
         const int nt = (ib - ia) * w;
         const float *ps = p.paf + (((size_t)frame * OPP_N_PAF + 2 * part) * h + ia) * w;
-        for (int t = threadIdx.x; t < nt; t += blockDim.x) Pf[t] = __ldg(ps + t), Pf[nt + t] = __ldg(ps + (size_t)h * w + t);
+        stage_async(Pf, ps, nt);
+        stage_async(Pf + nt, ps + (size_t)h * w, nt);
     }
+    stage_wait();
     __syncthreads();
 
     // ---- which blocks can hold a peak at all?  A pixel of feature cell (r, c) is filtered from the 3x3
@@ -868,20 +891,46 @@ __device__ void std_sort_desc(Cand *v, int n)
 #define HR_SCORE 19
 #define HR_NPARTS 20
 
+// Person assembly for one frame (src/paf.cpp:177-262) + output (:292-310), run by the limb CTA that
+// finished last.  Everything it needs (connection counts, all connections, peak x/y/score) is staged
+// into shared memory in two parallel round trips; the order-dependent part then runs in one warp
+// without touching global memory, and the output is written by the whole CTA.
 __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem_raw)
 {
-    int *hr = reinterpret_cast<int *>(smem_raw + p.off_href);     // [capH][21]
-    float *s_score = reinterpret_cast<float *>(smem_raw + p.off_score);
-    opp_conn_t *s_conn = reinterpret_cast<opp_conn_t *>(smem_raw + p.off_conn); // [capP]
-    __shared__ int s_state[8]; // n, hist_max, flags, merges, n_out
+    int *hr = reinterpret_cast<int *>(smem_raw + p.off_href);                   // [capH][21]
+    float3 *s_pk = reinterpret_cast<float3 *>(smem_raw + p.off_score);          // [n_peaks] x, y, score (score_in_smem)
+    opp_conn_t *s_conn = reinterpret_cast<opp_conn_t *>(smem_raw + p.off_conn); // all connections of the frame, or one limb's
+    int *s_keep = reinterpret_cast<int *>(smem_raw + p.off_keep);               // [capH] surviving humans, output order
+    __shared__ int s_state[8];                                                  // n, -, flags, merges, n_out
+    __shared__ int s_nc[OPP_N_PAIRS], s_coff[OPP_N_PAIRS + 1];
     const int capH = p.capH, capP = p.capP;
     const int *pofs = p.part_ofs + frame * (OPP_N_PARTS + 1);
     const int n_peaks = __ldcg(pofs + OPP_N_PARTS);
     const opp_peak_t *peaks = p.peaks + (size_t)frame * OPP_N_PARTS * capP;
-    if (p.score_in_smem)
-        for (int t = threadIdx.x; t < n_peaks; t += blockDim.x) s_score[t] = __ldcg(&peaks[t].score);
-    if (threadIdx.x < 8) s_state[threadIdx.x] = 0;
+    const bool all_conns = p.conns_in_smem != 0, pk_smem = p.score_in_smem != 0;
+    if (threadIdx.x < OPP_N_PAIRS) s_nc[threadIdx.x] = __ldcg(p.n_conns + frame * OPP_N_PAIRS + threadIdx.x);
+    if (threadIdx.x >= 32 && threadIdx.x < 40) s_state[threadIdx.x - 32] = 0;
+    if (pk_smem)
+        for (int t = threadIdx.x; t < n_peaks; t += blockDim.x)
+            s_pk[t] = make_float3((float)__ldcg(&peaks[t].x), (float)__ldcg(&peaks[t].y), __ldcg(&peaks[t].score));
     __syncthreads();
+    if (threadIdx.x == 0) {
+        int o = 0;
+        for (int l = 0; l < OPP_N_PAIRS; ++l) s_coff[l] = o, o += s_nc[l];
+        s_coff[OPP_N_PAIRS] = o;
+    }
+    __syncthreads();
+    if (all_conns) {
+        for (int l = 0; l < OPP_N_PAIRS; ++l) {
+            const opp_conn_t *g = p.conns + ((size_t)frame * OPP_N_PAIRS + l) * capP;
+            for (int t = threadIdx.x; t < s_nc[l]; t += blockDim.x) {
+                opp_conn_t c;
+                c.cid1 = __ldcg(&g[t].cid1), c.cid2 = __ldcg(&g[t].cid2), c.score = __ldcg(&g[t].score);
+                s_conn[s_coff[l] + t] = c;
+            }
+        }
+        __syncthreads();
+    }
 
     const int lane = threadIdx.x & 31;
     int n = 0, hist_max = 0, flags = 0, merges = 0;
@@ -890,22 +939,13 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
             flags |= OPP_FLAG_UB_PEAK_INDEX;
             return 0.f;
         }
-        return p.score_in_smem ? s_score[id] : __ldcg(&peaks[id].score);
+        return pk_smem ? s_pk[id].z : __ldcg(&peaks[id].score);
     };
-    for (int pair_id = 0; pair_id < OPP_N_PAIRS; ++pair_id) {
-        const int nconn = __ldcg(p.n_conns + frame * OPP_N_PAIRS + pair_id);
-        const opp_conn_t *gconn = p.conns + ((size_t)frame * OPP_N_PAIRS + pair_id) * capP;
-        __syncthreads();
-        for (int t = threadIdx.x; t < nconn; t += blockDim.x) {
-            s_conn[t].cid1 = __ldcg(&gconn[t].cid1);
-            s_conn[t].cid2 = __ldcg(&gconn[t].cid2);
-            s_conn[t].score = __ldcg(&gconn[t].score);
-        }
-        __syncthreads();
-        if (threadIdx.x >= 32) continue; // warp 0 runs the order-dependent part
+    // one limb's connections, in acceptance order; warp 0 only
+    auto do_limb = [&](int pair_id, const opp_conn_t *cl, int nconn) {
         const int part1 = c_pair_a[pair_id], part2 = c_pair_b[pair_id];
         for (int k = 0; k < nconn; ++k) {
-            const opp_conn_t conn = s_conn[k];
+            const opp_conn_t conn = cl[k];
             // for (auto hr : human_refs) if (hr.touches(...)) hr_ids.push_back(hr.id)   src/paf.cpp:195-199
             int n_hits = 0, hit0 = -1, hit1 = -1;
             for (int base = 0; base < n && n_hits < 2; base += 32) {
@@ -932,8 +972,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
                         h1[HR_SCORE] = __float_as_int(__fadd_rn(sc, __fadd_rn(peak_score(conn.cid2), conn.score)));
                     }
                 }
-                // keep the UB flag warp-uniform
-                flags |= __shfl_sync(0xffffffffu, flags, 0);
+                flags |= __shfl_sync(0xffffffffu, flags, 0); // keep the UB flag warp-uniform
             } else if (n_hits >= 2) {
                 if (hit0 < 0 || hit0 >= hist_max || hit1 < 0 || hit1 >= hist_max) {
                     flags |= OPP_FLAG_UB_STALE_INDEX;
@@ -995,16 +1034,28 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
             }
             __syncwarp();
         }
+    };
+
+    if (all_conns) {
+        if (threadIdx.x < 32)
+            for (int pair_id = 0; pair_id < OPP_N_PAIRS; ++pair_id) do_limb(pair_id, s_conn + s_coff[pair_id], s_nc[pair_id]);
+    } else { // capacities too large to stage every limb at once: one limb at a time
+        for (int pair_id = 0; pair_id < OPP_N_PAIRS; ++pair_id) {
+            const opp_conn_t *g = p.conns + ((size_t)frame * OPP_N_PAIRS + pair_id) * capP;
+            __syncthreads();
+            for (int t = threadIdx.x; t < s_nc[pair_id]; t += blockDim.x) {
+                opp_conn_t c;
+                c.cid1 = __ldcg(&g[t].cid1), c.cid2 = __ldcg(&g[t].cid2), c.score = __ldcg(&g[t].score);
+                s_conn[t] = c;
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) do_limb(pair_id, s_conn, s_nc[pair_id]);
+        }
     }
-    if (threadIdx.x == 0) s_state[0] = n, s_state[2] = flags, s_state[3] = merges;
-    __syncthreads();
-    n = s_state[0];
-    // src/paf.cpp:253-260 filter (order kept), :292-310 output
-    opp_human_t *out = p.humans + (size_t)frame * capH;
-    int *out_parts = p.href_parts + (size_t)frame * capH * OPP_N_PARTS;
+
+    // src/paf.cpp:253-260 filter (order kept)
     if (threadIdx.x < 32) {
         int n_out = 0;
-        int uflags = 0;
         for (int base = 0; base < n; base += 32) {
             const int q = base + lane;
             bool keep = false;
@@ -1014,39 +1065,45 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
                 keep = !(np < 4 || __fdiv_rn(sc, (float)np) < p.thr_human);
             }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (keep) {
-                const int o = n_out + __popc(m & ((1u << lane) - 1));
-                opp_human_t hu;
-                for (int i = 0; i < OPP_N_PARTS; ++i) {
-                    const int id = hr[q * HR_WORDS + HR_PART + i];
-                    out_parts[o * OPP_N_PARTS + i] = id;
-                    opp_body_part_t bp;
-                    bp.has_value = 0, bp.pad_[0] = bp.pad_[1] = bp.pad_[2] = 0, bp.x = bp.y = bp.score = 0.f;
-                    if (id != -1) {
-                        bp.has_value = 1;
-                        if (id < 0 || id >= n_peaks) {
-                            uflags |= OPP_FLAG_UB_PEAK_INDEX;
-                        } else {
-                            bp.x = (float)__ldcg(&peaks[id].x);
-                            bp.y = (float)__ldcg(&peaks[id].y);
-                            bp.score = __ldcg(&peaks[id].score);
-                        }
-                    }
-                    hu.parts[i] = bp;
-                }
-                hu.score = __int_as_float(hr[q * HR_WORDS + HR_SCORE]);
-                out[o] = hu;
-            }
+            if (keep) s_keep[n_out + __popc(m & ((1u << lane) - 1))] = q;
             n_out += __popc(m);
         }
-        for (int o = 16; o > 0; o >>= 1) uflags |= __shfl_xor_sync(0xffffffffu, uflags, o);
-        if (lane == 0) {
-            p.n_humans[frame] = n_out;
-            const int fl = s_state[2] | uflags;
-            if (fl) atomicOr(p.flags + frame, fl);
-            p.stats[frame * 4 + 0] = n;
-            p.stats[frame * 4 + 1] = s_state[3];
+        if (lane == 0) s_state[0] = n, s_state[2] = flags, s_state[3] = merges, s_state[4] = n_out;
+    }
+    __syncthreads();
+    // src/paf.cpp:292-310 output: one thread per (human, part)
+    const int n_out = s_state[4];
+    opp_human_t *out = p.humans + (size_t)frame * capH;
+    int *out_parts = p.href_parts + (size_t)frame * capH * OPP_N_PARTS;
+    int uflags = 0;
+    for (int it = threadIdx.x; it < n_out * OPP_N_PARTS; it += blockDim.x) {
+        const int o = it / OPP_N_PARTS, i = it - o * OPP_N_PARTS;
+        const int q = s_keep[o];
+        const int id = hr[q * HR_WORDS + HR_PART + i];
+        out_parts[o * OPP_N_PARTS + i] = id;
+        opp_body_part_t bp;
+        bp.has_value = 0, bp.pad_[0] = bp.pad_[1] = bp.pad_[2] = 0, bp.x = bp.y = bp.score = 0.f;
+        if (id != -1) {
+            bp.has_value = 1;
+            if (id < 0 || id >= n_peaks) {
+                uflags |= OPP_FLAG_UB_PEAK_INDEX;
+            } else if (pk_smem) {
+                const float3 pk = s_pk[id];
+                bp.x = pk.x, bp.y = pk.y, bp.score = pk.z;
+            } else {
+                bp.x = (float)__ldcg(&peaks[id].x), bp.y = (float)__ldcg(&peaks[id].y), bp.score = __ldcg(&peaks[id].score);
+            }
         }
+        out[o].parts[i] = bp;
+        if (i == 0) out[o].score = __int_as_float(hr[q * HR_WORDS + HR_SCORE]);
+    }
+    uflags = __syncthreads_or(uflags);
+    if (threadIdx.x == 0) {
+        p.n_humans[frame] = n_out;
+        const int fl = s_state[2] | uflags;
+        if (fl) atomicOr(p.flags + frame, fl);
+        p.stats[frame * 4 + 0] = s_state[0];
+        p.stats[frame * 4 + 1] = s_state[3];
     }
 }
 
@@ -1083,13 +1140,14 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const K3Params p)
         const float *gpy = gpx + h * w;
         const float *px_plane = gpx, *py_plane = gpy;
         if (p.paf_in_smem) {
-            for (int t = tid; t < 2 * h * w; t += blockDim.x) s_paf[t] = __ldg(gpx + t);
+            stage_async(s_paf, gpx, 2 * h * w); // the x and y channels of a limb are adjacent planes
             px_plane = s_paf, py_plane = s_paf + h * w;
         }
         for (int t = tid; t < na; t += blockDim.x) s_pa[t] = make_int2(__ldcg(&peaks[ofs_a + t].x), __ldcg(&peaks[ofs_a + t].y));
         for (int t = tid; t < nb; t += blockDim.x) s_pb[t] = make_int2(__ldcg(&peaks[ofs_b + t].x), __ldcg(&peaks[ofs_b + t].y));
         for (int t = tid; t < 2 * capP; t += blockDim.x) s_used[t] = 0;
         if (tid < 16) s_misc[tid] = 0;
+        stage_wait();
         __syncthreads();
 
         const int H = p.g.H, W = p.g.W;

@@ -66,9 +66,9 @@ struct K3Params {
     int *flags;            // [n]
     int *href_parts;       // [n][capH][18]
     int *stats;            // [n][4] partial humans, merges, total candidates, total pairs
-    int paf_in_smem, cand_in_smem, score_in_smem;
+    int paf_in_smem, cand_in_smem, score_in_smem, conns_in_smem;
     // shared-memory carve-up (byte offsets)
-    int off_paf, off_pk, off_cand, off_used, off_misc, off_href, off_score, off_conn;
+    int off_paf, off_pk, off_cand, off_used, off_misc, off_href, off_score, off_conn, off_keep;
     float thr_vec, thr_human;
 };
 
