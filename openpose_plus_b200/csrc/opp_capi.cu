@@ -47,6 +47,7 @@ struct Slot {
     opp_human_t *d_humans = nullptr;
     int *d_n_humans = nullptr;
     int *d_href_parts = nullptr;
+    unsigned long long *d_times = nullptr; // OPP_TRACE: per (frame, limb) phase stamps of the limb kernel
     // pinned results
     opp_human_t *h_humans = nullptr;
     int *h_n_humans = nullptr, *h_flags = nullptr;
@@ -167,6 +168,10 @@ void plan_k3_smem(opp_handle_s *h)
     p.score_in_smem = off + pk_bytes <= budget / 2;
     p.off_score = (int)off;
     if (p.score_in_smem) off += pk_bytes;
+    const size_t owner_bytes = (size_t)OPP_N_PARTS * capP * sizeof(int);
+    p.owner_in_smem = p.conns_in_smem && p.score_in_smem && off + owner_bytes <= budget / 2;
+    p.off_owner = (int)off;
+    if (p.owner_in_smem) off += owner_bytes;
     h->k3_smem = phase1 > off ? phase1 : off;
 }
 
@@ -175,7 +180,7 @@ int free_slot(opp_handle_s *h, Slot &s)
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_conf), cudaFree(s.d_paf), cudaFree(s.d_hwc), cudaFree(s.d_conf_up), cudaFree(s.d_counters);
     cudaFree(s.d_pk_key), cudaFree(s.d_peaks), cudaFree(s.d_part_ofs), cudaFree(s.d_conns), cudaFree(s.d_n_conns);
-    cudaFree(s.d_cand), cudaFree(s.d_humans), cudaFree(s.d_n_humans), cudaFree(s.d_href_parts);
+    cudaFree(s.d_cand), cudaFree(s.d_humans), cudaFree(s.d_n_humans), cudaFree(s.d_href_parts), cudaFree(s.d_times);
     cudaFreeHost(s.h_humans), cudaFreeHost(s.h_n_humans), cudaFreeHost(s.h_flags);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -204,8 +209,11 @@ int alloc_slot(opp_handle_s *h, Slot &s)
     CU(cudaEventCreate(&s.ev_done));
     CU(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
-    if (h->trace)
+    if (h->trace) {
         for (auto &e : s.tr) CU(cudaEventCreate(&e));
+        CU(cudaMalloc(&s.d_times, (B * OPP_N_PAIRS * 12 + 4096 * 8) * sizeof(unsigned long long)));
+        CU(cudaMemset(s.d_times, 0, (B * OPP_N_PAIRS * 12 + 4096 * 8) * sizeof(unsigned long long)));
+    }
     CU(cudaMalloc(&s.d_conf, B * OPP_N_HEAT * hw * sizeof(float)));
     CU(cudaMalloc(&s.d_paf, B * OPP_N_PAF * hw * sizeof(float)));
     CU(cudaMalloc(&s.d_counters, h->counters_ints * sizeof(int)));
@@ -514,6 +522,7 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     K2Params k2{};
     fill_k2(h, s, conf, conf_up_for_k2, n, fuse_up, k2);
     if (fuse_up) k2.paf = paf, k2.up_conf = b.conf_up, k2.up_paf = b.paf_up;
+    if (s.d_times && n == 1) k2.times = s.d_times + (size_t)c.max_batch * OPP_N_PAIRS * 12;
     int *d_flags = cnt_flags(h, s);
     if (h->fast_k2) {
         CU(launch_k2_fast(k2, n, st));
@@ -534,6 +543,7 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     k3.n_humans = dev_out ? b.n_humans : s.d_n_humans;
     k3.flags = d_flags;
     k3.href_parts = s.d_href_parts, k3.stats = cnt_stats(h, s);
+    k3.times = s.d_times;
     k3.thr_vec = 0.05f, k3.thr_human = 0.4f; // THRESH_VECTOR_SCORE, THRESH_HUMAN_SCORE, src/paf.cpp:61,64
     CU(launch_k3(k3, n, h->k3_smem, st));
     h->launches += 1;
@@ -621,6 +631,36 @@ int opp_wait(opp_handle_t h, int ticket)
         const bool up = s.batch.conf_up || s.batch.paf_up;
         for (int i = 0; i < 6; ++i)
             if (i >= 2 || up) cudaEventElapsedTime(&t[i], h->trace_base, s.tr[i]);
+        if (s.d_times && s.n_frames == 1) { // phase stamps of the limb kernel, relative to the earliest CTA start
+            unsigned long long t[OPP_N_PAIRS * 12];
+            cudaMemcpy(t, s.d_times, sizeof t, cudaMemcpyDeviceToHost);
+            unsigned long long t0 = ~0ull;
+            for (int l = 0; l < OPP_N_PAIRS; ++l)
+                if (t[l * 12] && t[l * 12] < t0) t0 = t[l * 12];
+            for (int l = 0; l < OPP_N_PAIRS; ++l) {
+                fprintf(stderr, "[opp k3] limb %2d:", l);
+                for (int k = 0; k < 10; ++k) fprintf(stderr, " %6.1f", t[l * 12 + k] ? (double)(t[l * 12 + k] - t0) * 1e-3 : -1.0);
+                fprintf(stderr, "  (us: start staged scored sorted matched | last: entered staged assembled filtered done)\n");
+            }
+            cudaMemset(s.d_times, 0, sizeof t);
+            // peak kernel: earliest start, latest of each phase over the CTAs
+            static unsigned long long t2[4096 * 8];
+            unsigned long long *d2 = s.d_times + (size_t)h->cfg.max_batch * OPP_N_PAIRS * 12;
+            cudaMemcpy(t2, d2, sizeof t2, cudaMemcpyDeviceToHost);
+            unsigned long long b0 = ~0ull, mx[8] = {0};
+            int nct = 0;
+            for (int cta = 0; cta < 4096; ++cta) {
+                if (!t2[cta * 8]) continue;
+                ++nct;
+                if (t2[cta * 8] < b0) b0 = t2[cta * 8];
+                for (int k = 0; k < 8; ++k)
+                    if (t2[cta * 8 + k] > mx[k]) mx[k] = t2[cta * 8 + k];
+            }
+            fprintf(stderr, "[opp k2] %d CTAs, latest stamp per phase (us after first CTA start):", nct);
+            for (int k = 0; k < 7; ++k) fprintf(stderr, " %6.1f", mx[k] ? (double)(mx[k] - b0) * 1e-3 : -1.0);
+            fprintf(stderr, "  (start staged analysed row-pass columns | last: entered finalized)\n");
+            cudaMemset(d2, 0, sizeof t2);
+        }
         fprintf(stderr, "[opp trace] ticket %d n=%d start %.3f | k1 %.3f-%.3f | k2 %.3f-%.3f | k3 -%.3f | copies -%.3f | done %.3f (ms)\n", s.ticket,
                 s.n_frames, t[6], t[0], t[1], t[2], t[3], t[4], t[5], t[7]);
     }

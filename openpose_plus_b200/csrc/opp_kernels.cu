@@ -249,46 +249,50 @@ __device__ void finalize_frame_peaks(const K2Params &p, int frame, int *s_keys /
 {
     const int W = p.g.W, H = p.g.H;
     const int capP = p.capP;
-    __shared__ int s_n[OPP_N_PARTS], s_ofs[OPP_N_PARTS + 1], s_over;
+    __shared__ int s_n[OPP_N_PARTS], s_ofs[OPP_N_PARTS + 1];
+    int over = 0;
     if (threadIdx.x < OPP_N_PARTS) {
         const int raw = __ldcg(p.cnt.pk_cnt + frame * OPP_N_PARTS + threadIdx.x);
         s_n[threadIdx.x] = min(raw, capP);
-        if (raw > capP) s_over = 1;
+        over = raw > capP;
     }
-    if (threadIdx.x == 32) s_over = 0;
-    __syncthreads();
+    over = __syncthreads_or(over);
     if (threadIdx.x == 0) {
         int ofs = 0;
         for (int part = 0; part < OPP_N_PARTS; ++part) s_ofs[part] = ofs, ofs += s_n[part];
         s_ofs[OPP_N_PARTS] = ofs;
     }
-    // all keys of the frame in one round trip
-    for (int part = 0; part < OPP_N_PARTS; ++part) {
-        const int *keys = p.pk_key + ((size_t)frame * OPP_N_PARTS + part) * capP;
-        for (int t = threadIdx.x; t < s_n[part]; t += blockDim.x) s_keys[part * capP + t] = __ldcg(keys + t);
+    __syncthreads();
+    // all keys of the frame in ONE round trip: flat index over the parts' lists
+    const int total = s_ofs[OPP_N_PARTS];
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        int part = 0;
+        while (part + 1 < OPP_N_PARTS && s_ofs[part + 1] <= t) ++part;
+        s_keys[t] = __ldcg(p.pk_key + ((size_t)frame * OPP_N_PARTS + part) * capP + (t - s_ofs[part]));
     }
     __syncthreads();
+    // rank inside the part = raster order; one more round trip for the scores
     opp_peak_t *out = p.peaks + (size_t)frame * OPP_N_PARTS * capP;
-    for (int part = 0; part < OPP_N_PARTS; ++part) {
-        const int n = s_n[part], ofs = s_ofs[part];
-        const int *k = s_keys + part * capP;
-        for (int t = threadIdx.x; t < n; t += blockDim.x) {
-            const int key = k[t];
-            int rank = 0;
-            for (int u = 0; u < n; ++u) rank += (k[u] < key);
-            const int y = key / W, x = key - y * W;
-            float score;
-            if (p.conf_up)
-                score = __ldcg(p.conf_up + ((size_t)frame * OPP_N_HEAT + part) * H * W + key);
-            else
-                score = upsample_at(p.g, p.conf + ((size_t)frame * OPP_N_HEAT + part) * p.g.h * p.g.w, y, x);
-            opp_peak_t pk;
-            pk.part_id = part, pk.x = x, pk.y = y, pk.score = score, pk.id = ofs + rank;
-            out[ofs + rank] = pk;
-        }
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        int part = 0;
+        while (part + 1 < OPP_N_PARTS && s_ofs[part + 1] <= t) ++part;
+        const int ofs = s_ofs[part], n = s_ofs[part + 1] - ofs;
+        const int *k = s_keys + ofs;
+        const int key = s_keys[t];
+        int rank = 0;
+        for (int u = 0; u < n; ++u) rank += (k[u] < key);
+        const int y = key / W, x = key - y * W;
+        float score;
+        if (p.conf_up)
+            score = __ldcg(p.conf_up + ((size_t)frame * OPP_N_HEAT + part) * H * W + key);
+        else
+            score = upsample_at(p.g, p.conf + ((size_t)frame * OPP_N_HEAT + part) * p.g.h * p.g.w, y, x);
+        opp_peak_t pk;
+        pk.part_id = part, pk.x = x, pk.y = y, pk.score = score, pk.id = ofs + rank;
+        out[ofs + rank] = pk;
     }
     if (threadIdx.x <= OPP_N_PARTS) p.part_ofs[frame * (OPP_N_PARTS + 1) + threadIdx.x] = s_ofs[threadIdx.x];
-    if (threadIdx.x == 0 && s_over) atomicOr(p.flags + frame, OPP_FLAG_PEAK_OVERFLOW);
+    if (threadIdx.x == 0 && over) atomicOr(p.flags + frame, OPP_FLAG_PEAK_OVERFLOW);
 }
 
 __device__ __forceinline__ bool tile_done_is_last(int *counter, int total)
@@ -391,11 +395,21 @@ struct NmsState {
 // SMs with the FP32 work by construction instead of relying on two kernels being co-scheduled (a
 // stand-alone resize next to this kernel serialises: both want every SM).  CTA 18 (background heat
 // map, PAF 36/37) only stores.
+__device__ __forceinline__ void stamp2(const K2Params &p, int slot)
+{
+    if (p.times && threadIdx.x == 0 && blockIdx.z == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.times[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+    }
+}
+
 template <int S, int R, bool STORE>
 __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peaks_fast(const K2Params p)
 {
     extern __shared__ __align__(16) float smem[];
     const int frame = blockIdx.z, part = blockIdx.y;
+    stamp2(p, 0);
     const bool compute = part < OPP_N_PARTS;
     const int tx = blockIdx.x % p.nxs, ty = blockIdx.x / p.nxs;
     const int h = p.g.h, w = p.g.w, H = S * h;
@@ -419,6 +433,7 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
     }
     stage_wait();
     __syncthreads();
+    stamp2(p, 1);
 
     // ---- which blocks can hold a peak at all?  A pixel of feature cell (r, c) is filtered from the 3x3
     // cells around it (R <= S, reflection included).  Every float operation of the filter is monotone
@@ -497,6 +512,7 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
         __syncthreads();
     }
 
+    stamp2(p, 2);
     // ---- row pass: one thread per (feature row, feature column) -> S outputs
     if (compute) {
         for (int it = threadIdx.x; it < nr * ncol; it += blockDim.x) {
@@ -520,6 +536,7 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
         }
     }
     __syncthreads();
+    stamp2(p, 3);
 
     const int xlo = S * jlo, xhi = S * jhi; // columns present in Rrow
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -658,8 +675,12 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
         }
     }
 
-    if (tile_done_is_last(p.cnt.k2_done + frame, p.nxs * p.nys * OPP_N_PARTS))
+    stamp2(p, 4);
+    if (tile_done_is_last(p.cnt.k2_done + frame, p.nxs * p.nys * OPP_N_PARTS)) {
+        stamp2(p, 5);
         finalize_frame_peaks(p, frame, reinterpret_cast<int *>(smem));
+        stamp2(p, 6);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -884,6 +905,15 @@ __device__ void std_sort_desc(Cand *v, int n)
         insertion_sort_range(v, v + n);
 }
 
+__device__ __forceinline__ void stamp(const K3Params &p, int frame, int pair_id, int slot)
+{
+    if (p.times && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.times[((size_t)frame * OPP_N_PAIRS + pair_id) * 12 + slot] = t;
+    }
+}
+
 // words of a partial human (human_ref_t, include/openpose-plus/human.h:57-77)
 #define HR_WORDS 21
 #define HR_ID 0
@@ -920,18 +950,25 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
         s_coff[OPP_N_PAIRS] = o;
     }
     __syncthreads();
-    if (all_conns) {
-        for (int l = 0; l < OPP_N_PAIRS; ++l) {
-            const opp_conn_t *g = p.conns + ((size_t)frame * OPP_N_PAIRS + l) * capP;
-            for (int t = threadIdx.x; t < s_nc[l]; t += blockDim.x) {
-                opp_conn_t c;
-                c.cid1 = __ldcg(&g[t].cid1), c.cid2 = __ldcg(&g[t].cid2), c.score = __ldcg(&g[t].score);
-                s_conn[s_coff[l] + t] = c;
-            }
+    if (all_conns) { // every connection of the frame in ONE round trip
+        const int total = s_coff[OPP_N_PAIRS];
+        for (int t = threadIdx.x; t < total; t += blockDim.x) {
+            int l = 0;
+            while (l + 1 < OPP_N_PAIRS && s_coff[l + 1] <= t) ++l;
+            const opp_conn_t *g = p.conns + ((size_t)frame * OPP_N_PAIRS + l) * capP + (t - s_coff[l]);
+            opp_conn_t c;
+            c.cid1 = __ldcg(&g->cid1), c.cid2 = __ldcg(&g->cid2), c.score = __ldcg(&g->score);
+            s_conn[t] = c;
         }
-        __syncthreads();
     }
+    // owner[peak id] = index of the partial human holding that peak (tree limbs only, see do_tree_limb)
+    int *s_owner = reinterpret_cast<int *>(smem_raw + p.off_owner);
+    const bool use_owner = p.owner_in_smem != 0;
+    if (use_owner)
+        for (int t = threadIdx.x; t < n_peaks; t += blockDim.x) s_owner[t] = -1;
+    __syncthreads();
 
+    stamp(p, frame, 18, 6);
     const int lane = threadIdx.x & 31;
     int n = 0, hist_max = 0, flags = 0, merges = 0;
     auto peak_score = [&](int id) -> float {
@@ -1036,9 +1073,63 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
         }
     };
 
+    // The 17 tree limbs (pair_id <= 16) in parallel, one lane per connection.  Each of them brings a
+    // part that no human holds yet (its second part appears as a second part nowhere earlier and as a
+    // first part only later, include/openpose-plus/coco.h:33-53) and the greedy matching uses every
+    // peak at most once per limb, so a connection touches at most ONE human (the one holding cid1),
+    // connections of a limb never touch each other's humans, and nothing has been erased yet (stored id
+    // == index).  The sequential loop of src/paf.cpp:192-248 therefore reduces to: look the owner of
+    // cid1 up, extend it, or append a new human in connection order (prefix sum over the lanes).
+    auto do_tree_limb = [&](int pair_id, const opp_conn_t *cl, int nconn) {
+        const int part1 = c_pair_a[pair_id], part2 = c_pair_b[pair_id];
+        for (int base = 0; base < nconn; base += 32) {
+            const int k = base + lane;
+            const bool on = k < nconn;
+            opp_conn_t conn;
+            conn.cid1 = conn.cid2 = -1, conn.score = 0.f;
+            if (on) conn = cl[k];
+            const bool id_ok = on && conn.cid1 >= 0 && conn.cid1 < n_peaks && conn.cid2 >= 0 && conn.cid2 < n_peaks;
+            const int q = id_ok ? s_owner[conn.cid1] : -1;
+            const bool fresh = on && q < 0;
+            const unsigned mnew = __ballot_sync(0xffffffffu, fresh);
+            const int slot = n + __popc(mnew & ((1u << lane) - 1));
+            if (on && q >= 0) {
+                int *h1 = hr + q * HR_WORDS;
+                if (h1[HR_PART + part2] != conn.cid2) {
+                    h1[HR_PART + part2] = conn.cid2;
+                    h1[HR_NPARTS] += 1;
+                    const float sc = __int_as_float(h1[HR_SCORE]);
+                    h1[HR_SCORE] = __float_as_int(__fadd_rn(sc, __fadd_rn(peak_score(conn.cid2), conn.score)));
+                    s_owner[conn.cid2] = q;
+                }
+            } else if (fresh) {
+                if (slot >= capH) {
+                    flags |= OPP_FLAG_HUMAN_OVERFLOW;
+                } else {
+                    int *hn = hr + slot * HR_WORDS;
+#pragma unroll
+                    for (int i = 0; i < OPP_N_PARTS; ++i) hn[HR_PART + i] = -1;
+                    hn[HR_PART + part1] = conn.cid1, hn[HR_PART + part2] = conn.cid2;
+                    hn[HR_ID] = slot, hn[HR_NPARTS] = 2;
+                    hn[HR_SCORE] = __float_as_int(__fadd_rn(__fadd_rn(peak_score(conn.cid1), peak_score(conn.cid2)), conn.score));
+                    if (id_ok) s_owner[conn.cid1] = slot, s_owner[conn.cid2] = slot;
+                }
+            }
+            n = min(n + __popc(mnew), capH);
+            __syncwarp();
+        }
+        if (n > hist_max) hist_max = n;
+        for (int o = 16; o > 0; o >>= 1) flags |= __shfl_xor_sync(0xffffffffu, flags, o);
+    };
+
     if (all_conns) {
         if (threadIdx.x < 32)
-            for (int pair_id = 0; pair_id < OPP_N_PAIRS; ++pair_id) do_limb(pair_id, s_conn + s_coff[pair_id], s_nc[pair_id]);
+            for (int pair_id = 0; pair_id < OPP_N_PAIRS; ++pair_id) {
+                if (use_owner && pair_id <= 16)
+                    do_tree_limb(pair_id, s_conn + s_coff[pair_id], s_nc[pair_id]);
+                else
+                    do_limb(pair_id, s_conn + s_coff[pair_id], s_nc[pair_id]);
+            }
     } else { // capacities too large to stage every limb at once: one limb at a time
         for (int pair_id = 0; pair_id < OPP_N_PAIRS; ++pair_id) {
             const opp_conn_t *g = p.conns + ((size_t)frame * OPP_N_PAIRS + pair_id) * capP;
@@ -1053,6 +1144,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
         }
     }
 
+    stamp(p, frame, 18, 7);
     // src/paf.cpp:253-260 filter (order kept)
     if (threadIdx.x < 32) {
         int n_out = 0;
@@ -1071,6 +1163,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
         if (lane == 0) s_state[0] = n, s_state[2] = flags, s_state[3] = merges, s_state[4] = n_out;
     }
     __syncthreads();
+    stamp(p, frame, 18, 8);
     // src/paf.cpp:292-310 output: one thread per (human, part)
     const int n_out = s_state[4];
     opp_human_t *out = p.humans + (size_t)frame * capH;
@@ -1133,6 +1226,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const K3Params p)
         cand1 = cand0 + capC;
     }
 
+    stamp(p, frame, pair_id, 0);
     int n_cand = 0;
     const long n_pairs = (long)na * nb;
     if (n_pairs > 0) {
@@ -1149,6 +1243,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const K3Params p)
         if (tid < 16) s_misc[tid] = 0;
         stage_wait();
         __syncthreads();
+        stamp(p, frame, pair_id, 1);
 
         const int H = p.g.H, W = p.g.W;
         int overflow = 0;
@@ -1210,6 +1305,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const K3Params p)
             if (tid == 0) atomicOr(p.flags + frame, OPP_FLAG_CAND_OVERFLOW);
             n_cand = min(n_cand, capC);
         }
+        stamp(p, frame, pair_id, 2);
 
         // ---- sort by score, descending, in std::sort's order.  With no equal scores the sorted order is
         // unique and a parallel rank sort gives it; with ties only the sequential emulation does.
@@ -1238,6 +1334,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const K3Params p)
             }
         }
 
+        stamp(p, frame, pair_id, 3);
         // ---- greedy matching in sorted order (src/paf.cpp:154-173)
         if (tid == 0) {
             opp_conn_t *conns = p.conns + ((size_t)frame * OPP_N_PAIRS + pair_id) * capP;
@@ -1258,7 +1355,12 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const K3Params p)
         p.n_conns[frame * OPP_N_PAIRS + pair_id] = 0;
     }
 
-    if (tile_done_is_last(p.cnt.k3_done + frame, OPP_N_PAIRS)) assemble_frame(p, frame, smem_raw);
+    stamp(p, frame, pair_id, 4);
+    if (tile_done_is_last(p.cnt.k3_done + frame, OPP_N_PAIRS)) {
+        stamp(p, frame, pair_id, 5);
+        assemble_frame(p, frame, smem_raw);
+        stamp(p, frame, pair_id, 9);
+    }
 }
 } // namespace
 

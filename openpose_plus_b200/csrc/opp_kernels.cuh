@@ -48,6 +48,7 @@ struct K2Params {
     int *flags;           // [n]
     float taps[OPP_MAX_KSIZE + 1];
     float thresh;
+    unsigned long long *times; // optional [ctas][8] %globaltimer phase stamps (debug, single frame), may be null
     float skip_thresh; // blocks whose 3x3 feature neighbourhood stays <= this cannot hold a peak; -inf disables the skip
 };
 
@@ -66,10 +67,11 @@ struct K3Params {
     int *flags;            // [n]
     int *href_parts;       // [n][capH][18]
     int *stats;            // [n][4] partial humans, merges, total candidates, total pairs
-    int paf_in_smem, cand_in_smem, score_in_smem, conns_in_smem;
+    int paf_in_smem, cand_in_smem, score_in_smem, conns_in_smem, owner_in_smem;
     // shared-memory carve-up (byte offsets)
-    int off_paf, off_pk, off_cand, off_used, off_misc, off_href, off_score, off_conn, off_keep;
+    int off_paf, off_pk, off_cand, off_used, off_misc, off_href, off_score, off_conn, off_keep, off_owner;
     float thr_vec, thr_human;
+    unsigned long long *times; // optional [n][19][12] %globaltimer stamps of the phases (debug), may be null
 };
 
 struct K1Params {
