@@ -53,6 +53,7 @@ struct Slot {
     int *h_n_humans = nullptr, *h_flags = nullptr;
     // in-flight batch
     bool busy = false;
+    bool direct_out = false; // results were written straight into the caller's pinned buffers
     int n_frames = 0;
     opp_batch_t batch{};
     float last_ms = 0.f;
@@ -85,6 +86,9 @@ struct opp_handle_s {
     bool trace = false;
     bool fuse_resize = true;
     bool k2_skip = true;
+    bool zero_copy_out = true;
+    int zero_copy_in_max = 0; // kernels reading pinned host maps in place: measured slower than staging them (kept for experiments)
+    int ingest_max = 4;       // up to this many frames, pinned host maps are pulled in by one kernel instead of memset + 2 DMA copies
     cudaEvent_t trace_base = nullptr;
 };
 
@@ -241,6 +245,17 @@ int *cnt_k2(opp_handle_s *h, Slot &s) { return s.d_counters + (size_t)h->cfg.max
 int *cnt_k3(opp_handle_s *h, Slot &s) { return cnt_k2(h, s) + h->cfg.max_batch; }
 int *cnt_stats(opp_handle_s *h, Slot &s) { return cnt_k3(h, s) + h->cfg.max_batch; }
 int *cnt_flags(opp_handle_s *h, Slot &s) { return cnt_stats(h, s) + (size_t)h->cfg.max_batch * 4; }
+
+// Device-visible alias of a pinned (cudaMallocHost / cudaHostRegister) host pointer, or null.
+void *mapped_host(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
 
 void choose_k2_tiles(opp_handle_s *h, int n_frames, bool store, int &tw, int &th)
 {
@@ -400,6 +415,9 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
         h->trace = getenv("OPP_TRACE") != nullptr;
         h->fuse_resize = getenv("OPP_NO_FUSE") == nullptr;
         h->k2_skip = getenv("OPP_K2_NOSKIP") == nullptr;
+        h->zero_copy_out = getenv("OPP_NO_ZEROCOPY_OUT") == nullptr;
+        if (const char *e = getenv("OPP_ZC_IN_MAX")) h->zero_copy_in_max = atoi(e);
+        if (const char *e = getenv("OPP_INGEST_MAX")) h->ingest_max = atoi(e);
         CU(cudaStreamCreateWithFlags(&h->timer_stream, cudaStreamNonBlocking));
         if (h->trace) {
             CU(cudaEventCreate(&h->trace_base));
@@ -434,7 +452,8 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     const size_t hw = (size_t)g.h * g.w, HW = (size_t)g.H * g.W;
     cudaStream_t st = s.stream;
     CU(cudaEventRecord(s.ev_start, st));
-    CU(cudaMemsetAsync(s.d_counters, 0, h->counters_ints * sizeof(int), st));
+    const bool ingest = b.in_mem == OPP_MEM_HOST && b.in_layout == OPP_LAYOUT_CHW && n <= h->ingest_max && mapped_host(b.conf) && mapped_host(b.paf);
+    if (!ingest) CU(cudaMemsetAsync(s.d_counters, 0, h->counters_ints * sizeof(int), st));
 
     // ---- inputs
     const float *conf = nullptr, *paf = nullptr;
@@ -455,6 +474,15 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
         CU(launch_hwc_to_chw(src, s.d_paf, n, OPP_N_PAF, g.h, g.w, st));
         h->launches += 2;
         conf = s.d_conf, paf = s.d_paf;
+    } else if (ingest) {
+        CU(launch_ingest((const float *)mapped_host(b.conf), s.d_conf, (size_t)n * OPP_N_HEAT * hw, (const float *)mapped_host(b.paf), s.d_paf,
+                         (size_t)n * OPP_N_PAF * hw, s.d_counters, (int)h->counters_ints, st));
+        h->launches += 1;
+        conf = s.d_conf, paf = s.d_paf;
+    } else if (b.in_mem == OPP_MEM_HOST && n <= h->zero_copy_in_max && mapped_host(b.conf) && mapped_host(b.paf)) {
+        // latency mode: a few frames in pinned memory are read by the kernels straight over PCIe
+        // (each feature row is staged into shared memory once per tile anyway); no copy is enqueued
+        conf = (const float *)mapped_host(b.conf), paf = (const float *)mapped_host(b.paf);
     } else if (b.in_mem == OPP_MEM_HOST) {
         CU(cudaMemcpyAsync(s.d_conf, b.conf, n * OPP_N_HEAT * hw * sizeof(float), in_kind, st));
         CU(cudaMemcpyAsync(s.d_paf, b.paf, n * OPP_N_PAF * hw * sizeof(float), in_kind, st));
@@ -539,9 +567,27 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     k3.cnt = k2.cnt;
     k3.cand_scratch = s.d_cand, k3.conns = s.d_conns, k3.n_conns = s.d_n_conns;
     const bool dev_out = b.out_mem == OPP_MEM_DEVICE;
-    k3.humans = dev_out ? b.humans : s.d_humans;
-    k3.n_humans = dev_out ? b.n_humans : s.d_n_humans;
+    // Host results: the assembly writes them over PCIe itself (mapped pinned memory) instead of three
+    // device-to-host copies behind the kernel - into the caller's buffers when those are pinned, else
+    // into the slot's pinned buffers (copied out in opp_wait).
+    s.direct_out = false;
+    opp_human_t *k3_humans = s.d_humans;
+    int *k3_counts = s.d_n_humans, *k3_flags_out = nullptr;
+    if (dev_out) {
+        k3_humans = b.humans, k3_counts = b.n_humans;
+    } else if (h->zero_copy_out) {
+        void *dh = mapped_host(b.humans), *dc = mapped_host(b.n_humans), *df = b.frame_flags ? mapped_host(b.frame_flags) : nullptr;
+        if (dh && dc && (df || !b.frame_flags)) {
+            k3_humans = (opp_human_t *)dh, k3_counts = (int *)dc, k3_flags_out = df ? (int *)df : s.h_flags;
+            s.direct_out = true;
+        } else {
+            k3_humans = s.h_humans, k3_counts = s.h_n_humans, k3_flags_out = s.h_flags;
+        }
+    }
+    k3.humans = k3_humans;
+    k3.n_humans = k3_counts;
     k3.flags = d_flags;
+    k3.flags_out = k3_flags_out;
     k3.href_parts = s.d_href_parts, k3.stats = cnt_stats(h, s);
     k3.times = s.d_times;
     k3.thr_vec = 0.05f, k3.thr_human = 0.4f; // THRESH_VECTOR_SCORE, THRESH_HUMAN_SCORE, src/paf.cpp:61,64
@@ -552,7 +598,7 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     // ---- results
     if (dev_out) {
         if (b.frame_flags) CU(cudaMemcpyAsync(b.frame_flags, d_flags, n * sizeof(int), cudaMemcpyDeviceToDevice, st));
-    } else {
+    } else if (!h->zero_copy_out) {
         CU(cudaMemcpyAsync(s.h_n_humans, s.d_n_humans, n * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(s.h_flags, d_flags, n * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(s.h_humans, s.d_humans, (size_t)n * c.max_humans * sizeof(opp_human_t), cudaMemcpyDeviceToHost, st));
@@ -665,7 +711,7 @@ int opp_wait(opp_handle_t h, int ticket)
                 s.n_frames, t[6], t[0], t[1], t[2], t[3], t[4], t[5], t[7]);
     }
     const opp_batch_t &b = s.batch;
-    if (b.out_mem == OPP_MEM_HOST) {
+    if (b.out_mem == OPP_MEM_HOST && !s.direct_out) {
         const int capH = h->cfg.max_humans;
         std::memcpy(b.n_humans, s.h_n_humans, s.n_frames * sizeof(int));
         if (b.frame_flags) std::memcpy(b.frame_flags, s.h_flags, s.n_frames * sizeof(int));

@@ -229,6 +229,35 @@ __global__ void __launch_bounds__(OPP_THREADS) k1_general(const K1Params p)
     }
 }
 
+// Latency-mode ingest: a few frames in pinned host memory are pulled over PCIe by the SMs (wide
+// coalesced loads, every request in flight at once) into the staging buffers, and the frame
+// counters are cleared by the same launch: one kernel instead of a memset and two DMA copies whose
+// fixed costs dominate at this size.
+__global__ void __launch_bounds__(OPP_THREADS) k0_ingest(const float *__restrict__ src0, float *__restrict__ dst0, size_t n0,
+                                                         const float *__restrict__ src1, float *__restrict__ dst1, size_t n1, int *counters, int n_counters)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < (size_t)n_counters; i += nth) counters[i] = 0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src0) | reinterpret_cast<uintptr_t>(src1) | reinterpret_cast<uintptr_t>(dst0) | reinterpret_cast<uintptr_t>(dst1)) & 15) == 0 &&
+                     ((n0 | n1) & 3) == 0;
+    if (vec) {
+        const size_t m0 = n0 >> 2, m1 = n1 >> 2;
+        for (size_t i = tid; i < m0 + m1; i += nth) {
+            if (i < m0)
+                reinterpret_cast<float4 *>(dst0)[i] = __ldcs(reinterpret_cast<const float4 *>(src0) + i);
+            else
+                reinterpret_cast<float4 *>(dst1)[i - m0] = __ldcs(reinterpret_cast<const float4 *>(src1) + (i - m0));
+        }
+    } else {
+        for (size_t i = tid; i < n0 + n1; i += nth) {
+            if (i < n0)
+                dst0[i] = __ldcs(src0 + i);
+            else
+                dst1[i - n0] = __ldcs(src1 + (i - n0));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(OPP_THREADS) k0_hwc_to_chw(const float *src, float *dst, int n, int C, int hw)
 {
     const size_t total = (size_t)n * C * hw;
@@ -1194,7 +1223,8 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
     if (threadIdx.x == 0) {
         p.n_humans[frame] = n_out;
         const int fl = s_state[2] | uflags;
-        if (fl) atomicOr(p.flags + frame, fl);
+        const int all = atomicOr(p.flags + frame, fl) | fl; // every other writer of this word finished before this CTA became last
+        if (p.flags_out) p.flags_out[frame] = all;
         p.stats[frame * 4 + 0] = s_state[0];
         p.stats[frame * 4 + 1] = s_state[3];
     }
@@ -1527,6 +1557,16 @@ cudaError_t launch_hwc_to_chw(const float *src, float *dst, int n, int C, int h,
     size_t blocks = (total + OPP_THREADS - 1) / OPP_THREADS;
     if (blocks > 148 * 32) blocks = 148 * 32;
     k0_hwc_to_chw<<<(unsigned)blocks, OPP_THREADS, 0, st>>>(src, dst, n, C, h * w);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ingest(const float *src0, float *dst0, size_t n0, const float *src1, float *dst1, size_t n1, int *counters, int n_counters,
+                          cudaStream_t st)
+{
+    size_t blocks = ((n0 + n1) / 4 + OPP_THREADS - 1) / OPP_THREADS;
+    if (blocks > (size_t)g_sm_count * 4) blocks = (size_t)g_sm_count * 4;
+    if (blocks < 1) blocks = 1;
+    k0_ingest<<<(unsigned)blocks, OPP_THREADS, 0, st>>>(src0, dst0, n0, src1, dst1, n1, counters, n_counters);
     return cudaGetLastError();
 }
 

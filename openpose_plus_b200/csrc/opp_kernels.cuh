@@ -64,7 +64,8 @@ struct K3Params {
     int *n_conns;          // [n][19]
     opp_human_t *humans;   // [n][capH]
     int *n_humans;         // [n]
-    int *flags;            // [n]
+    int *flags;            // [n] device flag words, OR-ed by every stage
+    int *flags_out;        // [n] optional: final flag word of the frame, written once by the assembly (may be mapped host memory)
     int *href_parts;       // [n][capH][18]
     int *stats;            // [n][4] partial humans, merges, total candidates, total pairs
     int paf_in_smem, cand_in_smem, score_in_smem, conns_in_smem, owner_in_smem;
@@ -93,4 +94,6 @@ cudaError_t launch_k2_generic(const K2Params &p, int n_frames, cudaStream_t st);
 cudaError_t launch_k3(const K3Params &p, int n_frames, size_t smem, cudaStream_t st);
 cudaError_t launch_k1(const K1Params &p, cudaStream_t st);
 cudaError_t launch_hwc_to_chw(const float *src, float *dst, int n, int C, int h, int w, cudaStream_t st);
+cudaError_t launch_ingest(const float *src0, float *dst0, size_t n0, const float *src1, float *dst1, size_t n1, int *counters, int n_counters,
+                          cudaStream_t st);
 cudaError_t opp_kernels_init(int max_smem_optin);
