@@ -120,3 +120,37 @@ def test_bad_arguments_are_errors(mods):
     conf, paf = synth.render_batch(3, n_people=1)
     with pytest.raises(capi.OppError):
         eng.process(conf, paf)           # more frames than max_batch
+
+
+def test_cpp_paf_processor_dropin(mods, tmp_path):
+    """A C++ program using only the reference's API (create_paf_processor + operator()) linked against
+    the library reproduces the reference build's golden humans."""
+    import subprocess
+    import conftest
+    Engine, capi, H = mods
+    root = conftest.ROOT
+    exe = str(tmp_path / "dropin_main")
+    libdir = os.path.join(root, "openpose_plus_b200")
+    cmd = ["g++", "-std=c++14", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "dropin_main.cpp"), "-o", exe,
+           "-L", libdir, "-l:libopp_b200.so", "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for name in ("frame_5p_368x432_k17", "frame_35p_368x432_k13", "frame_6p_300x400_k17"):
+        g = np.load(os.path.join(GOLD, name + ".npz"))
+        fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+        with open(fin, "wb") as f:
+            f.write(g["geom"].astype(np.int32).tobytes())
+            f.write(np.int32(2).tobytes())
+            for _ in range(2):
+                f.write(np.ascontiguousarray(g["conf"], np.float32).tobytes())
+                f.write(np.ascontiguousarray(g["paf"], np.float32).tobytes())
+        r = subprocess.run([exe, fin, fout], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        raw = open(fout, "rb").read()
+        off = 0
+        for _ in range(2):
+            m = int(np.frombuffer(raw, np.int32, 1, off)[0])
+            off += 4
+            humans = np.frombuffer(raw, capi.HUMAN_DT, m, off)
+            off += m * 292
+            assert H.humans_equal(humans, g["humans_ref"]) is None, name
