@@ -39,6 +39,23 @@ K2_BYTES_PER_FRAME = 4 * 19 * OUT_H * OUT_W                      # 12 082 176
 METRIC = "post-process frames/sec @368x432 COCO-18"
 
 
+def ncu_traffic(name):
+    """dram read + write bytes per launch from the committed ncu capture of that kernel (profiles/), or None."""
+    import csv
+    path = os.path.join(ROOT, "profiles", name)
+    try:
+        rows = list(csv.reader(open(path)))
+        d = {h: (v, u) for h, v, u in zip(rows[0], rows[2], rows[1])}
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v, u = d[key]
+            tot += float(v.replace(",", "")) * scale[u]
+        return tot
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -156,6 +173,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--slots", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -308,6 +326,42 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         lat_p50 = float(t[0])
 
+    # ---- the other BASELINE.json configurations, short runs (device-resident maps), rank 0 at N=1 only
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        from openpose_plus_b200 import synth
+
+        def other_config(fh, fw, people, batch, materialize, steps=40, **kw):
+            conf, paf = synth.render_batch(batch, n_people=people, feat_h=fh, feat_w=fw, seed0=2000, pool=8)
+            dc, dp = torch.from_numpy(conf).to(dev), torch.from_numpy(paf).to(dev)
+            e2 = Engine(fh, fw, max_batch=batch, device=local, n_slots=S, **kw)
+            ups = [(torch.empty((batch, 19, 8 * fh, 8 * fw), device=dev), torch.empty((batch, 38, 8 * fh, 8 * fw), device=dev)) for _ in range(S)] if materialize else None
+
+            def go(n):
+                infl = []
+                for k in range(n):
+                    if len(infl) == S:
+                        e2.wait(infl.pop(0))
+                    extra = dict(conf_up=ups[k % S][0], paf_up=ups[k % S][1]) if materialize else {}
+                    infl.append(e2.submit(dc, dp, **extra))
+                for t in infl:
+                    e2.wait(t)
+            go(5)
+            torch.cuda.synchronize()
+            e2._check(e2.L.opp_timer_start(e2.h))
+            go(steps)
+            ms = float(e2.L.opp_timer_stop(e2.h))
+            e2.close()
+            del ups
+            torch.cuda.empty_cache()
+            return steps * batch / (ms * 1e-3)
+
+        other = {
+            "736x864_b32_12people": {"materialised": other_config(92, 108, 12, 32, True), "skeleton_only": other_config(92, 108, 12, 32, False), "unit": "frames/s"},
+            "368x432_b64_crowded_32people": {"materialised": other_config(46, 54, 32, 64, True, max_humans=256),
+                                             "skeleton_only": other_config(46, 54, 32, 64, False, max_humans=256), "unit": "frames/s"},
+        }
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.oracle import Reference, ref_available
@@ -337,7 +391,7 @@ def main():
     if rank == 0:
         N = world
         h2d = BATCH * (19 + 38) * FEAT_H * FEAT_W * 4
-        d2h = BATCH * (eng.max_humans * 292 + 8)
+        d2h = int(BATCH * 8 + 292 * float(np.mean(outs[0][1])) * BATCH)  # counts + flags + the humans actually found, written over PCIe by the assembly kernel
         line = {
             "metric": METRIC, "value": N * frames / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": N, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -348,12 +402,14 @@ def main():
                        "sharding": "frames sharded over ranks, no collective, host gather"},
             "wall_ms_per_step": wall_ms / args.steps,
             "e2e": {"value": N * e_frames / (e_wall_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "device_event_value": N * e_frames / (e_dev_ms * 1e-3), "note": "pinned host maps in, skeletons out, wall clock"},
+                    "device_event_value": N * e_frames / (e_dev_ms * 1e-3), "note": "pinned host maps in (cudaMemcpyAsync H2D), skeletons out (written into pinned host memory by the assembly kernel), wall clock between synchronisation points"},
             "fused": {"value": N * f_frames / (f_dev_ms * 1e-3), "unit": "frames/s", "note": "skeletons only (C++ paf_processor contract): up-sampled maps never written to HBM"},
             "latency_ms_p50": lat_p50,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k2_peaks_fast<8,8,STORE> (resize of the 19+38 maps fused into smooth + NMS + peak list)",
-                         "achieved": k2s_gbs, "peak": peak, "unit": "GB/s", "frac": k2s_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "achieved": k2s_gbs, "peak": peak, "unit": "GB/s", "frac": k2s_gbs / peak, "traffic": ncu_traffic("r1_final_k2store_ncu_raw.csv"),
+                         "traffic_source": "profiles/r1_final_k2store_ncu_raw.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one 64-frame launch)",
+                         "algorithmic_bytes_per_launch": K1_BYTES_PER_FRAME * BATCH, "peak_source": peak_src,
                          "ms_per_launch": k2s_ms, "algorithmic_bytes_per_frame": K1_BYTES_PER_FRAME,
                          "note": "algorithmic bytes = 4*57*(h*w + H*W): feature maps read once, up-sampled maps written once; the smoothed / pooled maps never touch HBM"},
             "roofline_k1": {"bound": "hbm", "kernel": "k1_replicate_chw<8> (stand-alone resize, used when the maps are requested without fusion)",
@@ -365,6 +421,8 @@ def main():
             "clocks": clocks,
             "parity_checked": parity,
         }
+        if other:
+            line["other_configs"] = other
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
