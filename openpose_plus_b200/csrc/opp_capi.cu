@@ -269,9 +269,9 @@ void choose_k2_tiles(opp_handle_s *h, int n_frames, bool store, int &tw, int &th
     (void)S;
     // three resident CTAs per SM (the kernel is compiled for that): each must stay under ~72 KB, and
     // row tiles of about 16 feature rows keep the last wave short
-    // (measured at 368x432: ~12 rows when the kernel also streams the up-sampled maps - short tiles
+    // (measured at 368x432: ~8 rows when the kernel also streams the up-sampled maps - short tiles
     // keep the store flow even - and ~23 rows in skeleton-only mode, where per-CTA fixed costs dominate)
-    const int target = store ? 12 : 23;
+    const int target = store ? 8 : 23;
     int nys = (g.h + target - 1) / target;
     th = (g.h + nys - 1) / nys;
     while ((k2_fast_smem_bytes(g, tw, th) > (size_t)72 * 1024 || th > 60) && th > 4) th = (th + 1) / 2;

@@ -464,6 +464,43 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
     __syncthreads();
     stamp2(p, 1);
 
+    // ---- store plan (STORE): thread = (16-byte column v of the tile, half of the S replicated rows).
+    // Units = (plane, feature row) in plane-major order (heat tile, then the two PAF tiles), so each
+    // CTA writes ONE contiguous stream at a time (DRAM pages); per unit a thread writes HALF rows of
+    // its column.  Units are issued all along the CTA's life - a few between the prologue phases,
+    // three per feature row of the column loop - so the store stream never pauses for a whole phase.
+    constexpr int HALF = S / 2;
+    const int X0 = S * ja, X1 = S * jb;
+    const int W4 = (S * w) >> 2, Wt4 = (X1 - X0) >> 2;
+    const bool st_on = STORE && (int)threadIdx.x < 2 * Wt4;
+    const int nrt = ib - ia, st_total = 3 * nrt;
+    float4 *ob_h = nullptr, *ob_p = nullptr;
+    int fcol = 0;
+    const size_t plane4 = (size_t)H * W4;
+    if (st_on) {
+        const int half = (int)threadIdx.x / Wt4, v = (int)threadIdx.x - half * Wt4;
+        fcol = ja + (4 * v) / S;
+        const size_t tofs = (size_t)(S * ia + half * HALF) * W4 + (X0 >> 2) + v;
+        ob_h = reinterpret_cast<float4 *>(p.up_conf) + ((size_t)frame * OPP_N_HEAT + part) * plane4 + tofs;
+        ob_p = reinterpret_cast<float4 *>(p.up_paf) + ((size_t)frame * OPP_N_PAF + 2 * part) * plane4 + tofs;
+    }
+    int st_unit = 0;
+    auto store_units = [&](int count) {
+        if (st_on) {
+            for (int rep = 0; rep < count && st_unit < st_total; ++rep, ++st_unit) {
+                const int plane = st_unit / nrt, r = st_unit - plane * nrt;
+                const float sv = plane == 0 ? L[(ia - ilo + r) * w + fcol] : Pf[((plane - 1) * nrt + r) * w + fcol];
+                float4 *o = (plane == 0 ? ob_h : ob_p + (size_t)(plane - 1) * plane4) + (size_t)r * S * W4;
+                const float4 val = make_float4(sv, sv, sv, sv);
+#pragma unroll
+                for (int j = 0; j < HALF; ++j) __stcs(o + (size_t)j * W4, val);
+            }
+        }
+    };
+    const int st_pro = STORE ? (st_total + 7) / 8 : 0; // units issued in each of the three prologue gaps
+    store_units(st_pro);
+
+
     // ---- which blocks can hold a peak at all?  A pixel of feature cell (r, c) is filtered from the 3x3
     // cells around it (R <= S, reflection included).  Every float operation of the filter is monotone
     // in its inputs and the taps are positive, so if those nine values are all <= t then the smoothed
@@ -472,7 +509,6 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
     // (column group x feature row) need not be computed and its pixels may stand as -inf for their
     // neighbours.  Exact for every input; dense maps simply have every block active.
     __shared__ unsigned long long s_act[64], s_need[64], s_blk[K2_FAST_MAX_WARPS];
-    const int X0 = S * ja, X1 = S * jb;
     const int ngroups = (X1 - X0 + 61) / 62;
     if (compute) {
         const float t_skip = p.skip_thresh;
@@ -542,6 +578,7 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
     }
 
     stamp2(p, 2);
+    store_units(st_pro);
     // ---- row pass: one thread per (feature row, feature column) -> S outputs
     if (compute) {
         for (int it = threadIdx.x; it < nr * ncol; it += blockDim.x) {
@@ -566,48 +603,14 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
     }
     __syncthreads();
     stamp2(p, 3);
+    store_units(st_pro);
 
     const int xlo = S * jlo, xhi = S * jhi; // columns present in Rrow
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float NINF = -CUDART_INF_F;
 
-    // ---- store plan (STORE): thread = (16-byte column v of the tile, half of the S replicated rows);
-    // per feature row it writes HALF rows of its column in each of the three planes, interleaved
-    // with the filter arithmetic of the same feature row.
-    constexpr int HALF = S / 2;
-    const int W4 = (S * w) >> 2, Wt4 = (X1 - X0) >> 2;
-    const bool st_on = STORE && (int)threadIdx.x < 2 * Wt4;
-    // Store order: plane after plane (heat tile, then the two PAF tiles), three feature rows per
-    // iteration of the column loop, so each CTA writes ONE contiguous stream at a time (DRAM pages).
-    const int nrt = ib - ia;
-    float4 *ob_h = nullptr, *ob_p = nullptr;
-    int fcol = 0;
-    const size_t plane4 = (size_t)H * W4;
-    if (st_on) {
-        const int half = (int)threadIdx.x / Wt4, v = (int)threadIdx.x - half * Wt4;
-        fcol = ja + (4 * v) / S;
-        const size_t tofs = (size_t)(S * ia + half * HALF) * W4 + (X0 >> 2) + v;
-        ob_h = reinterpret_cast<float4 *>(p.up_conf) + ((size_t)frame * OPP_N_HEAT + part) * plane4 + tofs;
-        ob_p = reinterpret_cast<float4 *>(p.up_paf) + ((size_t)frame * OPP_N_PAF + 2 * part) * plane4 + tofs;
-    }
-    int st_unit = 0;
-    auto store_rows = [&]() {
-        if (st_on) {
-#pragma unroll
-            for (int rep = 0; rep < 3; ++rep, ++st_unit) {
-                const int plane = st_unit / nrt, r = st_unit - plane * nrt;
-                const float sv = plane == 0 ? L[(ia - ilo + r) * w + fcol] : Pf[((plane - 1) * nrt + r) * w + fcol];
-                float4 *o = (plane == 0 ? ob_h : ob_p + (size_t)(plane - 1) * plane4) + (size_t)r * S * W4;
-                const float4 val = make_float4(sv, sv, sv, sv);
-#pragma unroll
-                for (int j = 0; j < HALF; ++j) __stcs(o + (size_t)j * W4, val);
-            }
-        }
-    };
-
     if (!compute || warp >= ngroups) { // store-only CTA (background) or a warp without a column group
-        if (STORE)
-            for (int i = ia; i < ib; ++i) store_rows();
+        if (STORE) store_units(st_total);
         if (!compute) return;
     } else {
         // ---- column pass + 3x3 max + threshold.  A warp walks down 64 image columns, two per lane: lane l
@@ -676,7 +679,7 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
             a0 = b0, b0 = c0, a1 = b1, b1 = c1;
         }
         for (int i = ia; i < ib; ++i) {
-            if (STORE) store_rows();
+            if (STORE) store_units(3);
             const bool top = i == 0, bot = i == h - 1;
             c0 = bot ? 0.f : ld0(i + 1), c1 = bot ? 0.f : ld1(i + 1);
             if (active(i)) {
@@ -704,6 +707,7 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
         }
     }
 
+    if (STORE) store_units(st_total);
     stamp2(p, 4);
     if (tile_done_is_last(p.cnt.k2_done + frame, p.nxs * p.nys * OPP_N_PARTS)) {
         stamp2(p, 5);
