@@ -166,7 +166,7 @@ void plan_k3_smem(opp_handle_s *h)
     p.off_href = 0, off += align_up((size_t)capH * 21 * sizeof(int), 16);
     p.off_keep = (int)off, off += align_up((size_t)capH * sizeof(int), 16);
     const size_t conn_all = (size_t)OPP_N_PAIRS * capP * sizeof(opp_conn_t), conn_one = (size_t)capP * sizeof(opp_conn_t);
-    const size_t pk_bytes = (size_t)OPP_N_PARTS * capP * 3 * sizeof(float);
+    const size_t pk_bytes = (size_t)OPP_N_PARTS * capP * sizeof(int2); // x | y << 16, score
     p.conns_in_smem = off + conn_all + pk_bytes <= (size_t)(budget * 0.45);
     p.off_conn = (int)off, off += align_up(p.conns_in_smem ? conn_all : conn_one, 16);
     p.score_in_smem = off + pk_bytes <= budget / 2;
@@ -347,6 +347,10 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
     const int k = c.gauss_kernel_size;
     if (c.n_joins != OPP_N_HEAT || c.n_connections != OPP_N_PAIRS) {
         set_err(nullptr, "opp_create: n_joins and n_connections must be 19 (include/openpose-plus.hpp:63)");
+        return OPP_ERR_INVALID;
+    }
+    if (c.out_h > 32767 || c.out_w > 32767) {
+        set_err(nullptr, "opp_create: output size is limited to 32767 x 32767");
         return OPP_ERR_INVALID;
     }
     if (c.feat_h < 2 || c.feat_w < 2 || c.out_h < c.feat_h || c.out_w < c.feat_w) {

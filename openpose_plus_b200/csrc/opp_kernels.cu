@@ -961,7 +961,7 @@ __device__ __forceinline__ void stamp(const K3Params &p, int frame, int pair_id,
 __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem_raw)
 {
     int *hr = reinterpret_cast<int *>(smem_raw + p.off_href);                   // [capH][21]
-    float3 *s_pk = reinterpret_cast<float3 *>(smem_raw + p.off_score);          // [n_peaks] x, y, score (score_in_smem)
+    int2 *s_pk = reinterpret_cast<int2 *>(smem_raw + p.off_score);              // [n_peaks] {x | y << 16, score bits} (score_in_smem)
     opp_conn_t *s_conn = reinterpret_cast<opp_conn_t *>(smem_raw + p.off_conn); // all connections of the frame, or one limb's
     int *s_keep = reinterpret_cast<int *>(smem_raw + p.off_keep);               // [capH] surviving humans, output order
     __shared__ int s_state[8];                                                  // n, -, flags, merges, n_out
@@ -975,7 +975,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
     if (threadIdx.x >= 32 && threadIdx.x < 40) s_state[threadIdx.x - 32] = 0;
     if (pk_smem)
         for (int t = threadIdx.x; t < n_peaks; t += blockDim.x)
-            s_pk[t] = make_float3((float)__ldcg(&peaks[t].x), (float)__ldcg(&peaks[t].y), __ldcg(&peaks[t].score));
+            s_pk[t] = make_int2(__ldcg(&peaks[t].x) | (__ldcg(&peaks[t].y) << 16), __float_as_int(__ldcg(&peaks[t].score)));
     __syncthreads();
     if (threadIdx.x == 0) {
         int o = 0;
@@ -1009,7 +1009,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
             flags |= OPP_FLAG_UB_PEAK_INDEX;
             return 0.f;
         }
-        return pk_smem ? s_pk[id].z : __ldcg(&peaks[id].score);
+        return pk_smem ? __int_as_float(s_pk[id].y) : __ldcg(&peaks[id].score);
     };
     // one limb's connections, in acceptance order; warp 0 only
     auto do_limb = [&](int pair_id, const opp_conn_t *cl, int nconn) {
@@ -1214,8 +1214,8 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
             if (id < 0 || id >= n_peaks) {
                 uflags |= OPP_FLAG_UB_PEAK_INDEX;
             } else if (pk_smem) {
-                const float3 pk = s_pk[id];
-                bp.x = pk.x, bp.y = pk.y, bp.score = pk.z;
+                const int2 pk = s_pk[id];
+                bp.x = (float)(pk.x & 0xffff), bp.y = (float)(pk.x >> 16), bp.score = __int_as_float(pk.y);
             } else {
                 bp.x = (float)__ldcg(&peaks[id].x), bp.y = (float)__ldcg(&peaks[id].y), bp.score = __ldcg(&peaks[id].score);
             }
