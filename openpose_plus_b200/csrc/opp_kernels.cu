@@ -738,13 +738,21 @@ __global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic(const K2Params p
     // Only pixels inside the image are smoothed; the filter halo reflects, the NMS halo outside the
     // image is -inf.  Indices of halo pixels whose centre is outside the image are reflected too
     // (harmless: those smoothed values are discarded).
+    int hot = 0;
     for (int t = threadIdx.x; t < IH * IW; t += blockDim.x) {
         const int yy = y0 - 1 - R + t / IW, xx = x0 - 1 - R + t % IW;
         int ry = reflect101(yy, H), rx = reflect101(xx, W);
         ry = clip_idx(ry, H), rx = clip_idx(rx, W);
-        in[t] = __ldcg(plane + (size_t)ry * W + rx);
+        const float v = __ldcg(plane + (size_t)ry * W + rx);
+        in[t] = v;
+        hot |= v > p.skip_thresh;
     }
-    __syncthreads();
+    // Same exact early-out as the fast kernel: the staged region is everything the tile's smoothed
+    // pixels depend on; if all of it is <= thresh * (1 - 2^-13) no pixel of the tile can be a peak.
+    if (!__syncthreads_or(hot)) {
+        if (tile_done_is_last(p.cnt.k2_done + frame, gridDim.x * OPP_N_PARTS)) finalize_frame_peaks(p, frame, reinterpret_cast<int *>(smem));
+        return;
+    }
     for (int t = threadIdx.x; t < IH * TW; t += blockDim.x) {
         const int r = t / TW, c = t % TW;      // output column x0-1+c, centred at in[r][c+R]
         const float *q = in + r * IW + c;      // q[j] = tap j
