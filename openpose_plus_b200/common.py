@@ -38,3 +38,46 @@ def keypoints_array(human, image_w, image_h):
     for idx, bp in human.body_parts.items():
         out[idx] = (bp.x * image_w, bp.y * image_h, bp.score)
     return out
+
+
+CocoColors = [(255, 0, 0), (255, 85, 0), (255, 170, 0), (255, 255, 0), (170, 255, 0), (85, 255, 0), (0, 255, 0), (0, 255, 85),
+              (0, 255, 170), (0, 255, 255), (0, 170, 255), (0, 85, 255), (0, 0, 255), (85, 0, 255), (170, 0, 255), (255, 0, 255),
+              (255, 0, 170), (255, 0, 85)]
+
+
+def _disc(img, cx, cy, r, color):
+    h, w = img.shape[:2]
+    y0, y1, x0, x1 = max(cy - r, 0), min(cy + r + 1, h), max(cx - r, 0), min(cx + r + 1, w)
+    if y0 >= y1 or x0 >= x1:
+        return
+    yy, xx = np.ogrid[y0:y1, x0:x1]
+    img[y0:y1, x0:x1][(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = color
+
+
+def _line(img, p0, p1, color, thickness):
+    n = int(max(abs(p1[0] - p0[0]), abs(p1[1] - p0[1]))) + 1
+    xs = np.linspace(p0[0], p1[0], n).round().astype(int)
+    ys = np.linspace(p0[1], p1[1], n).round().astype(int)
+    r = max(thickness // 2, 0)
+    for x, y in zip(xs, ys):
+        _disc(img, int(x), int(y), r, color)
+
+
+def draw_humans(npimg, humans, imgcopy=False):
+    """Skeleton overlay like the reference's draw_humans (openpose_plus/inference/common.py:144-165) and
+    draw_human (examples/vis.cpp:56-81): a dot per detected part, a line per rendered limb.  numpy only."""
+    if imgcopy:
+        npimg = np.copy(npimg)
+    image_h, image_w = npimg.shape[:2]
+    for human in humans:
+        centers = {}
+        for i in range(18):
+            if i not in human.body_parts:
+                continue
+            bp = human.body_parts[i]
+            centers[i] = (int(bp.x * image_w + 0.5), int(bp.y * image_h + 0.5))
+            _disc(npimg, centers[i][0], centers[i][1], 3, CocoColors[i])
+        for pair_order, (a, b) in enumerate(CocoPairsRender):
+            if a in centers and b in centers:
+                _line(npimg, centers[a], centers[b], CocoColors[pair_order], 3)
+    return npimg

@@ -154,3 +154,16 @@ def test_host_gather_world_size_2_gloo(tmp_path):
            "--master-port", "29731", str(w), ROOT]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "GATHER_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_draw_humans_marks_parts_and_limbs():
+    from openpose_plus_b200.common import draw_humans, CocoColors
+    from openpose_plus_b200.post_process import humans_from_records
+    rec = np.zeros(1, capi.HUMAN_DT)
+    rec[0]["parts"][1] = (1, [0, 0, 0], 100.0, 50.0, 0.9)
+    rec[0]["parts"][2] = (1, [0, 0, 0], 150.0, 80.0, 0.9)
+    rec[0]["parts"][10] = (1, [0, 0, 0], 300.0, 300.0, 0.9)
+    img = draw_humans(np.zeros((368, 432, 3), np.uint8), humans_from_records(rec, 368, 432))
+    assert tuple(img[300, 300]) == CocoColors[10]          # isolated part: its dot
+    assert tuple(img[65, 125]) == CocoColors[0]            # midpoint of limb 0 (neck - right shoulder)
+    assert img[200, 50].sum() == 0
