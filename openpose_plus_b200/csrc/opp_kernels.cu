@@ -55,6 +55,32 @@ __device__ __forceinline__ void stage_async(float *sdst, const float *gsrc, int 
 }
 __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// TMA bulk load (cp.async.bulk global -> shared, completion on an mbarrier): ONE instruction moves a
+// whole contiguous tile; the copy engine does the rest while the CTA sets up.  Requires 16-byte
+// aligned source, destination and size.  bulk_load() is called by a single thread after
+// bulk_init(); every thread that reads the tile calls bulk_wait() first.
+__device__ __forceinline__ void bulk_init(unsigned long long *mbar)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(float *sdst, const float *gsrc, unsigned bytes, unsigned long long *mbar)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(mbar), d = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gsrc), "r"(bytes), "r"(a)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_wait(unsigned long long *mbar, unsigned phase)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(a), "r"(phase) : "memory");
+    } while (!ok);
+}
+
 // One sample of the area-mode up-sampled map (cv::resize INTER_AREA, dst >= src): horizontal 2-tap
 // on the two source rows, then vertical 2-tap.  Same float operations as the row-buffer form.
 __device__ __forceinline__ float upsample_at(const OppGeom &g, const float *plane, int y, int x)
@@ -1271,12 +1297,23 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const K3Params p)
     stamp(p, frame, pair_id, 0);
     int n_cand = 0;
     const long n_pairs = (long)na * nb;
+    __shared__ unsigned long long s_mbar;
+    bool paf_bulk = false;
     if (n_pairs > 0) {
         const float *gpx = p.paf + ((size_t)frame * OPP_N_PAF + cx) * h * w;
         const float *gpy = gpx + h * w;
         const float *px_plane = gpx, *py_plane = gpy;
         if (p.paf_in_smem) {
-            stage_async(s_paf, gpx, 2 * h * w); // the x and y channels of a limb are adjacent planes
+            // the x and y channels of a limb are adjacent planes: one contiguous tile of 2*h*w floats
+            paf_bulk = ((reinterpret_cast<uintptr_t>(gpx) | (uintptr_t)(2 * h * w * sizeof(float))) & 15) == 0;
+            if (paf_bulk) {
+                if (tid == 0) {
+                    bulk_init(&s_mbar);
+                    bulk_load(s_paf, gpx, (unsigned)(2 * h * w * sizeof(float)), &s_mbar);
+                }
+            } else {
+                stage_async(s_paf, gpx, 2 * h * w);
+            }
             px_plane = s_paf, py_plane = s_paf + h * w;
         }
         for (int t = tid; t < na; t += blockDim.x) s_pa[t] = make_int2(__ldcg(&peaks[ofs_a + t].x), __ldcg(&peaks[ofs_a + t].y));
@@ -1284,7 +1321,8 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const K3Params p)
         for (int t = tid; t < 2 * capP; t += blockDim.x) s_used[t] = 0;
         if (tid < 16) s_misc[tid] = 0;
         stage_wait();
-        __syncthreads();
+        __syncthreads(); // also publishes the mbarrier initialisation to the waiting threads
+        if (paf_bulk) bulk_wait(&s_mbar, 0);
         stamp(p, frame, pair_id, 1);
 
         const int H = p.g.H, W = p.g.W;

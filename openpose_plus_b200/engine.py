@@ -65,7 +65,8 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     def submit(self, conf, paf, layout=capi.LAYOUT_CHW, conf_up=None, paf_up=None, up_layout=capi.LAYOUT_CHW, out=None):
         """conf [n,19,h,w] / paf [n,38,h,w] (or channels-last), numpy (host) or CUDA tensors.
-        Returns a ticket for wait().  `out` may carry pre-allocated (humans, n_humans, flags) arrays."""
+        Returns a ticket for wait().  `out` may carry pre-allocated (humans, n_humans, flags): numpy arrays
+        (host results) or CUDA uint8/int32 tensors of the same byte sizes (results stay on the device)."""
         dev = _is_device(conf)
         if isinstance(conf, np.ndarray):
             conf = np.ascontiguousarray(conf, np.float32)
@@ -77,7 +78,7 @@ class Engine:
         b = capi.Batch()
         b.conf, b.paf, b.n_frames = _ptr(conf), _ptr(paf), n
         b.in_mem = capi.MEM_DEVICE if dev else capi.MEM_HOST
-        b.in_layout, b.out_mem = layout, capi.MEM_HOST
+        b.in_layout, b.out_mem = layout, (capi.MEM_DEVICE if _is_device(humans) else capi.MEM_HOST)
         b.humans, b.n_humans, b.frame_flags = _ptr(humans), _ptr(counts), _ptr(flags)
         b.conf_up, b.paf_up, b.up_layout = _ptr(conf_up), _ptr(paf_up), up_layout
         t = C.c_int(-1)

@@ -154,3 +154,52 @@ def test_cpp_paf_processor_dropin(mods, tmp_path):
             humans = np.frombuffer(raw, capi.HUMAN_DT, m, off)
             off += m * 292
             assert H.humans_equal(humans, g["humans_ref"]) is None, name
+
+
+def test_device_outputs_and_channels_last_device_input(mods):
+    """Results can stay on the device (out_mem = DEVICE) and channels-last device tensors are accepted."""
+    import torch
+    Engine, capi, H = mods
+    conf, paf = synth.render_batch(5, n_people=4, seed0=900)
+    eng = Engine(46, 54, max_batch=5)
+    ref_h, ref_c, ref_f = eng.process(conf, paf)
+    d_h = torch.zeros((5, eng.max_humans * 292), dtype=torch.uint8, device="cuda")
+    d_c = torch.full((5,), -1, dtype=torch.int32, device="cuda")
+    d_f = torch.full((5,), -1, dtype=torch.int32, device="cuda")
+    dc = torch.from_numpy(np.ascontiguousarray(conf.transpose(0, 2, 3, 1))).cuda()
+    dp = torch.from_numpy(np.ascontiguousarray(paf.transpose(0, 2, 3, 1))).cuda()
+    eng.process(dc, dp, layout=capi.LAYOUT_HWC, out=(d_h, d_c, d_f))
+    torch.cuda.synchronize()
+    assert np.array_equal(d_c.cpu().numpy(), ref_c) and np.array_equal(d_f.cpu().numpy(), ref_f)
+    got = d_h.cpu().numpy().view(capi.HUMAN_DT).reshape(5, eng.max_humans)
+    for f in range(5):
+        assert H.humans_equal(got[f, :ref_c[f]], ref_h[f, :ref_c[f]]) is None
+
+
+def test_pageable_host_buffers_and_slot_reuse(mods):
+    """Plain (pageable) numpy inputs/outputs take the staged path; many more batches than slots."""
+    Engine, capi, H = mods
+    conf, paf = synth.render_batch(6, n_people=3, seed0=950)
+    eng = Engine(46, 54, max_batch=2, n_slots=2)
+    ref = [eng.process(conf[i:i + 2], paf[i:i + 2]) for i in range(0, 6, 2)]
+    tickets = []
+    outs = []
+    for rep in range(4):
+        for i in range(0, 6, 2):
+            if len(tickets) == 2:
+                outs.append(eng.wait(tickets.pop(0)))
+            tickets.append(eng.submit(conf[i:i + 2], paf[i:i + 2]))
+    while tickets:
+        outs.append(eng.wait(tickets.pop(0)))
+    assert len(outs) == 12
+    for k, (h, c, f) in enumerate(outs):
+        rh, rc, rf = ref[k % 3]
+        assert np.array_equal(c, rc) and np.array_equal(f, rf)
+        for j in range(2):
+            assert H.humans_equal(h[j, :c[j]], rh[j, :rc[j]]) is None
+    with pytest.raises(capi.OppError):   # third submit without a wait: no free slot
+        t1, t2 = eng.submit(conf[:2], paf[:2]), eng.submit(conf[:2], paf[:2])
+        try:
+            eng.submit(conf[:2], paf[:2])
+        finally:
+            eng.wait(t1), eng.wait(t2)
