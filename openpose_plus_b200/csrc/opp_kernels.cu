@@ -390,21 +390,27 @@ template <int S, int R>
 __device__ __forceinline__ void row_taps(const float *__restrict__ k, float a, float b, float c, float a_sp, float c_sp,
                                          float (&out)[S])
 {
+    // value of the up-sampled row at offset o from the start of this feature column (o in [-R, S-1+R])
+    auto src = [&](int o) -> float {
+        if (o < 0) return (R == S && o == -S) ? a_sp : a;
+        if (o < S) return b;
+        return (R == S && o == 2 * S - 1) ? c_sp : c;
+    };
 #pragma unroll
     for (int q = 0; q < S; ++q) {
-        float s = 0.f;
+        float s;
+        if (R == 1) { // OpenCV's SymmRowSmallFilter, ksize 3
+            s = __fadd_rn(__fmul_rn(src(q), k[1]), __fmul_rn(__fadd_rn(src(q - 1), src(q + 1)), k[2]));
+        } else if (R == 2) { // ksize 5
+            s = __fadd_rn(__fmul_rn(src(q), k[2]), __fmul_rn(__fadd_rn(src(q - 1), src(q + 1)), k[3]));
+            s = __fadd_rn(s, __fmul_rn(__fadd_rn(src(q - 2), src(q + 2)), k[4]));
+        } else { // RowFilter: taps left to right
+            s = 0.f;
 #pragma unroll
-        for (int j = 0; j <= 2 * R; ++j) {
-            const int o = q + j - R; // offset of the tap from the start of this feature column
-            float v;
-            if (o < 0)
-                v = (R == S && o == -S) ? a_sp : a;
-            else if (o < S)
-                v = b;
-            else
-                v = (R == S && o == 2 * S - 1) ? c_sp : c;
-            const float pr = __fmul_rn(k[j], v);
-            s = (j == 0) ? pr : __fadd_rn(s, pr);
+            for (int j = 0; j <= 2 * R; ++j) {
+                const float pr = __fmul_rn(k[j], src(q + j - R));
+                s = (j == 0) ? pr : __fadd_rn(s, pr);
+            }
         }
         out[q] = s;
     }
@@ -1486,8 +1492,8 @@ static cudaError_t launch_k2_fast_sr(const K2Params &p, int n_frames, size_t sme
 
 bool k2_fast_supported(const OppGeom &g)
 {
-    if (g.S != 8 || g.h < 2 || g.w < 2) return false;
-    return g.K == 17 || g.K == 13 || g.K == 9;
+    // integer scale 8 or 4 on both axes, Gaussian radius within one feature cell
+    return (g.S == 8 || g.S == 4) && g.R <= g.S && g.h >= 2 && g.w >= 2;
 }
 
 size_t k2_fast_smem_bytes(const OppGeom &g, int tw, int th)
@@ -1506,11 +1512,12 @@ cudaError_t launch_k2_fast(const K2Params &p, int n_frames, cudaStream_t st)
     size_t need = smem;
     if ((size_t)OPP_N_PARTS * p.capP * sizeof(int) > need) need = (size_t)OPP_N_PARTS * p.capP * sizeof(int);
     if (need > (size_t)g_max_smem) return cudaErrorInvalidValue;
-    switch (p.g.K) {
-    case 17: return launch_k2_fast_sr<8, 8>(p, n_frames, need, st);
-    case 13: return launch_k2_fast_sr<8, 6>(p, n_frames, need, st);
-    case 9: return launch_k2_fast_sr<8, 4>(p, n_frames, need, st);
-    }
+#define K2_CASE(S_, R_)                                                       \
+    if (p.g.S == S_ && p.g.R == R_) return launch_k2_fast_sr<S_, R_>(p, n_frames, need, st);
+    K2_CASE(8, 8) K2_CASE(8, 6) K2_CASE(8, 4)               // k = 17, 13, 9: the kernel sizes the reference's demos and scripts use
+    K2_CASE(8, 7) K2_CASE(8, 5) K2_CASE(8, 3) K2_CASE(8, 2) K2_CASE(8, 1) K2_CASE(8, 0)
+    K2_CASE(4, 4) K2_CASE(4, 3) K2_CASE(4, 2) K2_CASE(4, 1) K2_CASE(4, 0)
+#undef K2_CASE
     return cudaErrorInvalidValue;
 }
 

@@ -81,3 +81,17 @@ def test_values_around_the_peak_threshold(mods):
         ys, xs = rng.integers(0, 46, 12), rng.integers(0, 54, 12)
         conf2[f, rng.integers(0, 18, 12), ys, xs] = rng.uniform(0.04, 0.9, 12).astype(np.float32)
     H.run_and_check(eng, orc, conf2, paf2, "background")
+
+
+def test_fast_path_all_kernel_sizes_and_scale_4(mods):
+    """Every (scale, kernel size) the integer-scale peak kernel is instantiated for: scale 8 with k = 1..17
+    and scale 4 with k = 1..9 (k <= 5 use OpenCV's symmetric-small row form, k = 1 is a copy).  Small kernels
+    on replicated maps tie whole plateaus, hence few people and large capacities."""
+    Engine, Oracle, H = mods
+    for (scale, k, people) in [(8, 15, 5), (8, 11, 5), (8, 7, 4), (8, 5, 1), (4, 9, 5), (4, 7, 5), (4, 5, 4), (4, 3, 1), (4, 1, 1)]:
+        conf, paf = synth.render_batch(2, n_people=people, seed0=800 + k)
+        oh, ow = 46 * scale, 54 * scale
+        eng = Engine(46, 54, oh, ow, gauss_kernel_size=k, max_batch=2, max_peaks_per_part=1024, max_cands_per_limb=65536, max_humans=2048)
+        orc = Oracle(46, 54, oh, ow, k)
+        H.run_and_check(eng, orc, conf, paf, "fast x%d k=%d" % (scale, k))
+        eng.close()
