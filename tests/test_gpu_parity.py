@@ -95,3 +95,20 @@ def test_fast_path_all_kernel_sizes_and_scale_4(mods):
         orc = Oracle(46, 54, oh, ow, k)
         H.run_and_check(eng, orc, conf, paf, "fast x%d k=%d" % (scale, k))
         eng.close()
+
+
+def test_small_and_odd_geometries_on_the_fast_path(mods):
+    """Tiny feature maps (down to 2x2) with noise: every pixel is within reach of an image border, so the
+    REFLECT_101 special taps, the halo clamps and the single-tile / multi-tile logic are all exercised."""
+    Engine, Oracle, H = mods
+    rng = np.random.default_rng(11)
+    for (fh, fw, scale, k) in [(2, 2, 8, 17), (2, 5, 8, 17), (3, 3, 8, 13), (5, 7, 8, 17), (7, 3, 8, 9), (9, 31, 8, 17), (33, 4, 8, 17),
+                               (2, 2, 4, 9), (6, 5, 4, 7), (13, 17, 4, 9), (60, 70, 8, 17), (20, 120, 8, 17)]:
+        n = 3
+        conf = (rng.random((n, 19, fh, fw), dtype=np.float32) ** 3).astype(np.float32)      # sparse-ish noise, some values above threshold
+        paf = (rng.random((n, 38, fh, fw), dtype=np.float32) * 2 - 1).astype(np.float32)
+        conf[1] *= 0.04                                                                      # one frame entirely below the threshold
+        eng = Engine(fh, fw, fh * scale, fw * scale, gauss_kernel_size=k, max_batch=n, max_peaks_per_part=1024, max_cands_per_limb=65536, max_humans=2048)
+        orc = Oracle(fh, fw, fh * scale, fw * scale, k)
+        H.run_and_check(eng, orc, conf, paf, "%dx%d x%d k=%d" % (fh, fw, scale, k))
+        eng.close()
