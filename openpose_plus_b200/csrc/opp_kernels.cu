@@ -557,9 +557,14 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
             if (lane_ == 0) s_act[r] = bits;
         }
         __syncthreads();
-        // ... dilated 3x3 on the bit rows (lane = feature row)
-        if (warp_ == 0) {
-            unsigned long long d[2];
+        // (2) active blocks: warp g owns column group g; lane = feature row; the 3x3 dilation of the bit rows
+        //     is done on the fly (rows r-1, r, r+1 OR-ed, then shifted left and right by one cell)
+        if (warp_ < ngroups) {
+            const int g = warp_;
+            const int xa = X0 + 62 * g, xb = min(xa + 62, X1) - 1;
+            const int ca = xa / S - jlo, cb = xb / S - jlo;
+            const unsigned long long dec = (cb - ca >= 63 ? ~0ull : ((1ull << (cb - ca + 1)) - 1)) << ca; // cells of the decided columns
+            unsigned long long blk = 0ull;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const int r = lane_ + 32 * k;
@@ -570,41 +575,23 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
                     if (r + 1 < nr) v |= s_act[r + 1];
                     v |= (v << 1) | (v >> 1);
                 }
-                d[k] = v;
+                blk |= (unsigned long long)__ballot_sync(0xffffffffu, (v & dec) != 0) << (32 * k);
             }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-                if (lane_ + 32 * k < nr) s_act[lane_ + 32 * k] = d[k];
+            if (lane_ == 0) s_blk[g] = blk;
         }
         __syncthreads();
-        // (2) active blocks per column group (one warp; lane = feature row) and (3) the cells the row pass must produce
-        if (warp_ == 0) {
-            unsigned long long dec[K2_FAST_MAX_WARPS], span[K2_FAST_MAX_WARPS];
-#pragma unroll
-            for (int g = 0; g < K2_FAST_MAX_WARPS; ++g) {
-                const int xa = X0 + 62 * g, xb = min(xa + 62, X1) - 1;
-                const int ca = xa / S - jlo, cb = xb / S - jlo;
-                const int sa = max(xa - 1, S * jlo) / S - jlo, sb = min(xb + 1, S * jhi - 1) / S - jlo;
-                dec[g] = g < ngroups ? ((cb - ca >= 63 ? ~0ull : ((1ull << (cb - ca + 1)) - 1)) << ca) : 0ull;
-                span[g] = g < ngroups ? ((sb - sa >= 63 ? ~0ull : ((1ull << (sb - sa + 1)) - 1)) << sa) : 0ull;
+        // (3) the cells the row pass must produce: every cell a live block reads (its 64 columns, rows r-1..r+1)
+        for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+            unsigned long long need = 0ull;
+            const unsigned long long near3 = (r > 0 ? 7ull << (r - 1) : 3ull); // rows r-1, r, r+1
+            for (int g = 0; g < ngroups; ++g) {
+                if (s_blk[g] & near3) {
+                    const int xa = X0 + 62 * g, xb = min(xa + 62, X1) - 1;
+                    const int sa = max(xa - 1, S * jlo) / S - jlo, sb = min(xb + 1, S * jhi - 1) / S - jlo;
+                    need |= (sb - sa >= 63 ? ~0ull : ((1ull << (sb - sa + 1)) - 1)) << sa;
+                }
             }
-            unsigned long long blk[K2_FAST_MAX_WARPS];
-#pragma unroll
-            for (int g = 0; g < K2_FAST_MAX_WARPS; ++g) {
-                const unsigned lo = __ballot_sync(0xffffffffu, lane_ < nr && (s_act[lane_] & dec[g]) != 0);
-                const unsigned hi = __ballot_sync(0xffffffffu, lane_ + 32 < nr && (s_act[min(lane_ + 32, 63)] & dec[g]) != 0);
-                blk[g] = (unsigned long long)lo | ((unsigned long long)hi << 32);
-                if (lane_ == 0) s_blk[g] = blk[g];
-            }
-            for (int r = lane_; r < nr; r += 32) {
-                unsigned long long need = 0ull;
-                const unsigned long long near3 = (r > 0 ? 7ull << (r - 1) : 3ull); // rows r-1, r, r+1
-#pragma unroll
-                for (int g = 0; g < K2_FAST_MAX_WARPS; ++g)
-                    if (blk[g] & near3) need |= span[g];
-                s_need[r] = need;
-            }
+            s_need[r] = need;
         }
         __syncthreads();
     }
