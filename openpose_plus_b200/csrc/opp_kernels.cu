@@ -822,6 +822,17 @@ __global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic(const K2Params p
 // accepted candidates, std::sort-order sort, greedy matching.  The last limb of a frame to finish
 // assembles the frame's humans.
 // ------------------------------------------------------------------------------------------------
+// roundpaf (src/paf.cpp:337): (int)(v + 0.5) with the add in double.  For 0 <= v < 2^23 the double sum
+// t + f + 0.5 (t = floor v, f = v - t, both exact in float) truncates to t + (f >= 0.5): no FP64 needed.
+__device__ __forceinline__ int round_paf(float v)
+{
+    if (v >= 0.f && v < 8388608.f) {
+        const int t = (int)v;
+        return t + (__fsub_rn(v, (float)t) >= 0.5f ? 1 : 0);
+    }
+    return (int)__dadd_rn((double)v, 0.5);
+}
+
 struct Cand {
     int i1, i2;
     float s;
@@ -1319,6 +1330,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const K3Params p)
         stamp(p, frame, pair_id, 1);
 
         const int H = p.g.H, W = p.g.W;
+        const int sshift = (p.g.S > 0 && (p.g.S & (p.g.S - 1)) == 0) ? 31 - __clz(p.g.S) : -1;
         int overflow = 0;
         for (long base = 0; base < n_pairs; base += blockDim.x) {
             const long idx = base + tid;
@@ -1329,8 +1341,12 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const K3Params p)
                 ia = (int)(idx / nb), ib = (int)(idx - (long)ia * nb);
                 const int2 A = s_pa[ia], B = s_pb[ib];
                 const int dx = B.x - A.x, dy = B.y - A.y;
-                const float norm = (float)sqrt((double)(dx * dx + dy * dy)); // src/paf.cpp:91
-                if (!((double)norm < 1e-12)) {
+                // norm = (float)sqrt((double)l2)  (src/paf.cpp:91).  Rounding sqrt to 53 and then to 24 bits equals
+                // rounding it to 24 bits directly (double rounding is innocuous for sqrt when 53 >= 2*24 + 2),
+                // so the single-precision IEEE sqrt gives the same float whenever l2 is exact in float.
+                const int l2 = dx * dx + dy * dy;
+                const float norm = l2 < (1 << 24) ? __fsqrt_rn((float)l2) : (float)sqrt((double)l2);
+                if (l2 != 0) { // `norm < 1e-12` is true only for coincident peaks
                     const float vx = __fdiv_rn((float)dx, norm), vy = __fdiv_rn((float)dy, norm);
                     const float step_x = __fdiv_rn((float)dx, 10.f), step_y = __fdiv_rn((float)dy, 10.f); // :321-322
                     float scores = 0.f;
@@ -1340,17 +1356,28 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const K3Params p)
                         // roundpaf(peak1.x + i * STEP_X): float mul, float add, double +0.5, truncate  :325-326,337
                         const float fx = __fadd_rn((float)A.x, __fmul_rn((float)i, step_x));
                         const float fy = __fadd_rn((float)A.y, __fmul_rn((float)i, step_y));
-                        int lx = (int)__dadd_rn((double)fx, 0.5), ly = (int)__dadd_rn((double)fy, 0.5);
+                        int lx = round_paf(fx), ly = round_paf(fy);
                         lx = clip_idx(lx, W), ly = clip_idx(ly, H);
-                        const float vpx = upsample_at(p.g, px_plane, ly, lx);
-                        const float vpy = upsample_at(p.g, py_plane, ly, lx);
+                        float vpx, vpy;
+                        if (sshift >= 0) { // replication by a power of two: one shared index, no integer division
+                            const int fi = (ly >> sshift) * w + (lx >> sshift);
+                            vpx = px_plane[fi], vpy = py_plane[fi];
+                        } else {
+                            vpx = upsample_at(p.g, px_plane, ly, lx);
+                            vpy = upsample_at(p.g, py_plane, ly, lx);
+                        }
                         const float score = __fadd_rn(__fmul_rn(vx, vpx), __fmul_rn(vy, vpy)); // :108-109
                         scores = __fadd_rn(scores, score);
                         cnt += (score > p.thr_vec);
                     }
                     // scores / STEP_PAF + std::min(0.0, 0.5 * height / norm - 1.0)   :115-116
-                    const double pen = __dsub_rn(__ddiv_rn(0.5 * (double)H, (double)norm), 1.0);
-                    crit2 = (float)__dadd_rn((double)__fdiv_rn(scores, 10.f), pen < 0.0 ? pen : 0.0);
+                    const float s10 = __fdiv_rn(scores, 10.f);
+                    if (norm <= 0.5f * (float)H) {
+                        crit2 = s10; // 0.5*H/norm >= 1 exactly, so the penalty is min(0.0, >= 0) = 0 and (float)((double)s10 + 0.0) == s10
+                    } else {
+                        const double pen = __dsub_rn(__ddiv_rn(0.5 * (double)H, (double)norm), 1.0);
+                        crit2 = (float)__dadd_rn((double)s10, pen < 0.0 ? pen : 0.0);
+                    }
                     accept = cnt > 8 && crit2 > 0.f;
                 }
             }
