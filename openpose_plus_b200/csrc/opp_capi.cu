@@ -689,8 +689,8 @@ int opp_wait(opp_handle_t h, int ticket)
                 if (t[l * 12] && t[l * 12] < t0) t0 = t[l * 12];
             for (int l = 0; l < OPP_N_PAIRS; ++l) {
                 fprintf(stderr, "[opp k3] limb %2d:", l);
-                for (int k = 0; k < 10; ++k) fprintf(stderr, " %6.1f", t[l * 12 + k] ? (double)(t[l * 12 + k] - t0) * 1e-3 : -1.0);
-                fprintf(stderr, "  (us: start staged scored sorted matched | last: entered staged assembled filtered done)\n");
+                for (int k = 0; k < 11; ++k) fprintf(stderr, " %6.1f", t[l * 12 + k] ? (double)(t[l * 12 + k] - t0) * 1e-3 : -1.0);
+                fprintf(stderr, "  (us: start staged scored sorted matched | last: entered staged assembled filtered done tree-limbs-done)\n");
             }
             cudaMemset(s.d_times, 0, sizeof t);
             // peak kernel: earliest start, latest of each phase over the CTAs

@@ -1035,8 +1035,10 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
     // owner[peak id] = index of the partial human holding that peak (tree limbs only, see do_tree_limb)
     int *s_owner = reinterpret_cast<int *>(smem_raw + p.off_owner);
     const bool use_owner = p.owner_in_smem != 0;
-    if (use_owner)
+    if (use_owner) {
         for (int t = threadIdx.x; t < n_peaks; t += blockDim.x) s_owner[t] = -1;
+        for (int t = threadIdx.x; t < capH * OPP_N_PARTS; t += blockDim.x) hr[(t / OPP_N_PARTS) * HR_WORDS + HR_PART + t % OPP_N_PARTS] = -1;
+    }
     __syncthreads();
 
     stamp(p, frame, 18, 6);
@@ -1177,9 +1179,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
                 if (slot >= capH) {
                     flags |= OPP_FLAG_HUMAN_OVERFLOW;
                 } else {
-                    int *hn = hr + slot * HR_WORDS;
-#pragma unroll
-                    for (int i = 0; i < OPP_N_PARTS; ++i) hn[HR_PART + i] = -1;
+                    int *hn = hr + slot * HR_WORDS; // part ids were preset to -1 by the whole CTA
                     hn[HR_PART + part1] = conn.cid1, hn[HR_PART + part2] = conn.cid2;
                     hn[HR_ID] = slot, hn[HR_NPARTS] = 2;
                     hn[HR_SCORE] = __float_as_int(__fadd_rn(__fadd_rn(peak_score(conn.cid1), peak_score(conn.cid2)), conn.score));
@@ -1190,12 +1190,15 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
             __syncwarp();
         }
         if (n > hist_max) hist_max = n;
-        for (int o = 16; o > 0; o >>= 1) flags |= __shfl_xor_sync(0xffffffffu, flags, o);
     };
 
     if (all_conns) {
         if (threadIdx.x < 32)
             for (int pair_id = 0; pair_id < OPP_N_PAIRS; ++pair_id) {
+                if (pair_id == 17) {
+                    for (int o = 16; o > 0; o >>= 1) flags |= __shfl_xor_sync(0xffffffffu, flags, o); // lanes diverged on UB / overflow flags
+                    stamp(p, frame, 18, 10);
+                }
                 if (use_owner && pair_id <= 16)
                     do_tree_limb(pair_id, s_conn + s_coff[pair_id], s_nc[pair_id]);
                 else
