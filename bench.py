@@ -130,8 +130,11 @@ def run_reference(args, rank):
     conf, paf = ring[0]
     geom = (FEAT_H, FEAT_W, OUT_H, OUT_W, KSIZE)
     if kind == "reference":
+        from oracle.oracle import ReferencePool
+        pool = ReferencePool(geom, min(cores, BATCH), fast=True)  # processors are built once, like a long-running caller would
+
         def step(n):
-            return Reference.time_frames(geom, conf[:n], paf[:n], repeat=1, threads=min(cores, n), fast=True)[0]
+            return pool.run(conf[:n], paf[:n])[0]
     else:
         from oracle.oracle import Oracle
         orc = Oracle(*geom)

@@ -200,6 +200,11 @@ class Reference:
             L.ref_time_frames.restype = C.c_double
             L.ref_time_frames.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
             L.ref_std_sort_desc.argtypes = [C.c_void_p, C.c_int]
+            L.ref_pool_create.restype = C.c_void_p
+            L.ref_pool_create.argtypes = [C.c_int] * 6
+            L.ref_pool_destroy.argtypes = [C.c_void_p]
+            L.ref_pool_run.restype = C.c_double
+            L.ref_pool_run.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_long)]
             cls._libs[fast] = L
         return cls._libs[fast]
 
@@ -236,3 +241,23 @@ class Reference:
         v = np.ascontiguousarray(cands, dtype=CAND_DT).copy()
         cls.lib().ref_std_sort_desc(v.ctypes.data, len(v))
         return v
+
+
+class ReferencePool:
+    """`threads` reference processors kept alive across calls; run() returns wall seconds for the frames given."""
+
+    def __init__(self, geom, threads, fast=True):
+        self.L = Reference.lib(fast)
+        self.p = self.L.ref_pool_create(*geom, threads)
+        self.threads = threads
+
+    def run(self, conf, paf):
+        conf, pc = _f32(conf)
+        paf, pp = _f32(paf)
+        tot = C.c_long(0)
+        return self.L.ref_pool_run(self.p, pc, pp, conf.shape[0], C.byref(tot)), tot.value
+
+    def __del__(self):
+        if getattr(self, "p", None):
+            self.L.ref_pool_destroy(self.p)
+            self.p = None

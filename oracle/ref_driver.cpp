@@ -96,6 +96,48 @@ double ref_time_frames(int feat_h, int feat_w, int out_h, int out_w, int ksize, 
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// A pool of processors kept across calls (constructing one allocates ~100 MB of scratch, which
+// is setup, not per-frame work): ref_pool_run times n_frames on the pool's threads.
+struct ref_pool {
+    int feat_h, feat_w;
+    std::vector<std::unique_ptr<paf_processor>> procs;
+};
+
+void *ref_pool_create(int feat_h, int feat_w, int out_h, int out_w, int ksize, int n_threads)
+{
+    stdout_silencer quiet;
+    ref_pool *p = new ref_pool{feat_h, feat_w, {}};
+    for (int t = 0; t < n_threads; ++t)
+        p->procs.emplace_back(create_paf_processor(feat_h, feat_w, out_h, out_w, n_joins, n_connections, ksize));
+    return p;
+}
+
+void ref_pool_destroy(void *pp) { delete static_cast<ref_pool *>(pp); }
+
+double ref_pool_run(void *pp, const float *conf, const float *paf, int n_frames, long *humans_total)
+{
+    stdout_silencer quiet;
+    ref_pool *p = static_cast<ref_pool *>(pp);
+    const size_t cs = (size_t)19 * p->feat_h * p->feat_w, ps = (size_t)38 * p->feat_h * p->feat_w;
+    std::atomic<long> next(0), total(0);
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> ths;
+    for (size_t t = 0; t < p->procs.size(); ++t)
+        ths.emplace_back([&, t] {
+            long local = 0;
+            for (;;) {
+                const long j = next.fetch_add(1);
+                if (j >= n_frames) break;
+                local += (long)(*p->procs[t])(conf + j * cs, paf + j * ps, false).size();
+            }
+            total += local;
+        });
+    for (auto &th : ths) th.join();
+    const auto t1 = std::chrono::steady_clock::now();
+    if (humans_total) *humans_total = total.load();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
 // The real thing the reference calls at src/paf.cpp:151-152.
 void ref_std_sort_desc(orc_cand_t *v, int n)
 {
