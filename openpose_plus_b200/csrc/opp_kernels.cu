@@ -234,6 +234,40 @@ __global__ void __launch_bounds__(128) k1_replicate_bulk(const K1Params p, int G
     if (threadIdx.x < G * S) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory must outlive the reads
 }
 
+// Channels-last output ([n, H, W, C], what the Python PostProcessor returns) at an integer scale: one
+// CTA per (feature row, tensor, frame) builds ONE output row (W pixels x C channels, 33 KB for the heat
+// maps and 66 KB for the PAFs at 432 columns) in shared memory - the S image rows of a feature row are
+// identical - and hands it to the copy engine S times (TMA bulk store, one cp.async.bulk per row).
+template <int S>
+__global__ void __launch_bounds__(OPP_THREADS) k1_replicate_hwc(const K1Params p)
+{
+    extern __shared__ __align__(128) float srow[]; // [W*C] output row, then [C][w] feature row
+    const int w = p.g.w, W = p.g.W, h = p.g.h, H = p.g.H;
+    const int i = blockIdx.x, f = blockIdx.z;
+    const bool second = blockIdx.y == 1;
+    const int C = second ? p.C2 : p.C;
+    const float *src = (second ? p.src2 : p.src) + (size_t)f * C * h * w + (size_t)i * w;
+    float *dst = (second ? p.dst2 : p.dst) + ((size_t)f * H + (size_t)i * S) * W * C;
+    float *feat = srow + (size_t)W * C;
+    for (int t = threadIdx.x; t < C * w; t += blockDim.x) {
+        const int c = t / w, x = t - c * w;
+        feat[t] = __ldg(src + (size_t)c * h * w + x);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < W * C; t += blockDim.x) {
+        const int x = t / C, c = t - x * C;
+        srow[t] = feat[c * w + x / S];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < S) {
+        const unsigned bytes = (unsigned)((size_t)W * C * sizeof(float));
+        bulk_store_row(dst + (size_t)threadIdx.x * W * C, srow, bytes);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory must outlive the reads
+    }
+}
+
 // Any geometry / layout: one thread per output element, table-driven 2x2-tap sample.
 __global__ void __launch_bounds__(OPP_THREADS) k1_general(const K1Params p)
 {
@@ -1579,6 +1613,19 @@ static bool k1_fast_ok(const K1Params &p)
 cudaError_t launch_k1(const K1Params &p, cudaStream_t st)
 {
     const OppGeom &g = p.g;
+    if (p.layout == OPP_LAYOUT_HWC && g.S == 8) {
+        const int Cmax = p.C2 > p.C ? p.C2 : p.C;
+        const size_t smem = ((size_t)g.W * Cmax + (size_t)Cmax * g.w) * sizeof(float);
+        const bool ok16 = (((size_t)g.W * p.C * 4) & 15) == 0 && (p.C2 == 0 || (((size_t)g.W * p.C2 * 4) & 15) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.dst) | reinterpret_cast<uintptr_t>(p.dst2)) & 15) == 0;
+        static int dyn_limit = 0;
+        if (!dyn_limit && allow_big_smem(k1_replicate_hwc<8>, &dyn_limit) != cudaSuccess) dyn_limit = -1;
+        if (ok16 && dyn_limit > 0 && smem <= (size_t)dyn_limit) {
+            dim3 grid(g.h, p.C2 ? 2 : 1, p.n);
+            k1_replicate_hwc<8><<<grid, OPP_THREADS, smem, st>>>(p);
+            return cudaGetLastError();
+        }
+    }
     static const int mode = getenv("OPP_K1_MODE") ? atoi(getenv("OPP_K1_MODE")) : 2; // 0 rows, 1 TMA bulk, 2 first version
     if (k1_fast_ok(p) && mode == 0 && 2 * (g.W >> 2) <= 224) {
         static const int G = getenv("OPP_K1_G") ? atoi(getenv("OPP_K1_G")) : 4; // feature rows per item: 32 output rows, 55 KB contiguous
