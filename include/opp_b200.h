@@ -100,7 +100,9 @@ typedef struct {
     int32_t in_mem;        /* OPP_MEM_HOST | OPP_MEM_DEVICE */
     int32_t in_layout;     /* OPP_LAYOUT_CHW | OPP_LAYOUT_HWC */
     int32_t out_mem;       /* where humans / n_humans / frame_flags live */
-    opp_human_t *humans;   /* [n, max_humans]; frame f's humans are humans[f*max_humans .. +n_humans[f]) */
+    opp_human_t *humans;   /* [n, max_humans]; frame f's humans are humans[f*max_humans .. +n_humans[f]).  Pinned host
+                            * buffers (opp_host_alloc / cudaHostRegister) are written directly by the GPU, pageable ones
+                            * through the slot's pinned staging; entries beyond n_humans[f] are left untouched */
     int32_t *n_humans;     /* [n] */
     int32_t *frame_flags;  /* [n] OPP_FLAG_* bits, may be NULL */
     /* Optional materialised up-sampled maps (DEVICE pointers), what the reference keeps in

@@ -1,16 +1,26 @@
 // Hand-written sm_100a kernels of the openpose-plus post-processing path.
 //
-//   K1  resize        area-mode up-sampling of the 19+38 maps          (src/post-process.h:24-49)
-//   K2  peaks         Gaussian smoothing + 3x3 max NMS + threshold     (src/post-process.h:51-111,155-203)
-//                     + raster-order peak list                          (src/post-process.h:190-198,205-213)
-//   K3  limbs         PAF line-integral scoring of candidate pairs     (src/paf.cpp:79-134,313-337)
-//       matching      std::sort order + greedy bipartite matching      (src/paf.cpp:136-175)
-//       assembly      person assembly + human_t output                 (src/paf.cpp:177-262,292-310)
+//   K2  k2_peaks_fast<S,R,STORE>   Gaussian smoothing + 3x3 max NMS + threshold      (src/post-process.h:51-111,155-203)
+//                                  + raster-order peak list                           (src/post-process.h:190-198,205-213)
+//                                  + (STORE) the x8 / x4 up-sampling of all 57 maps   (src/post-process.h:24-49) written
+//                                    from inside the same kernel; exact skipping of blocks provably below the threshold
+//       k2_peaks_generic           the same stage for any kernel size / any scale, on a materialised heat map
+//   K1  k1_replicate_chw / _hwc    stand-alone up-sampling, channels-first (streaming stores) and channels-last (TMA
+//       k1_general                 bulk stores); table-driven 2x2-tap version for non-integer scales
+//   K3  k3_limbs                   PAF line-integral scoring of candidate pairs      (src/paf.cpp:79-134,313-337)
+//                                  std::sort order + greedy bipartite matching       (src/paf.cpp:136-175)
+//                                  person assembly + human_t output (last limb CTA)  (src/paf.cpp:177-262,292-310)
+//   K0  k0_ingest, k0_hwc_to_chw   input staging helpers
 //
 // All arithmetic that decides an integer output is written with explicit round-to-nearest
 // intrinsics in the reference's operation order (the library is also built with -fmad=false), so
 // results are bit-identical to a strict-IEEE build of the reference.  No tensor cores: nothing here
 // is a dense contraction.  Citations are relative to /root/reference.
+//
+// Debug / experiment switches (environment, read once): OPP_TRACE (event + phase-stamp timelines),
+// OPP_K2_NOSKIP, OPP_NO_FUSE, OPP_FORCE_GENERIC, OPP_K2_TW / OPP_K2_TH (tile size), OPP_K1_MODE
+// (0 persistent lean stores, 1 TMA bulk stores, 2 = default streaming stores), OPP_K1_G, OPP_K1_CTAS,
+// OPP_NO_ZEROCOPY_OUT, OPP_INGEST_MAX, OPP_ZC_IN_MAX, OPP_NO_PRIORITY.
 #include "opp_kernels.cuh"
 
 #include <math_constants.h>
