@@ -92,6 +92,21 @@ struct opp_handle_s {
     cudaEvent_t trace_base = nullptr;
 };
 
+// Entry points run on the handle's device and give the caller its own current device back.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 #define CU(call)                                                                                      \
     do {                                                                                              \
         cudaError_t e_ = (call);                                                                      \
@@ -322,7 +337,7 @@ void opp_host_free(void *p)
 void opp_destroy(opp_handle_t h)
 {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard guard_(h->device);
     for (auto &s : h->slots) free_slot(h, s);
     if (h->timer_t0) cudaEventDestroy(h->timer_t0);
     if (h->timer_t1) cudaEventDestroy(h->timer_t1);
@@ -373,6 +388,8 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
     opp_handle_s *h = new opp_handle_s();
     h->cfg = c;
     int rc = OPP_OK;
+    int caller_dev = -1;
+    cudaGetDevice(&caller_dev);
     auto body = [&]() -> int {
         if (c.device >= 0)
             CU(cudaSetDevice(c.device));
@@ -440,8 +457,10 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
     if (rc != OPP_OK) {
         g_err = h->err;
         opp_destroy(h);
+        if (caller_dev >= 0) cudaSetDevice(caller_dev);
         return rc;
     }
+    if (caller_dev >= 0) cudaSetDevice(caller_dev);
     *out = h;
     return OPP_OK;
 }
@@ -628,7 +647,7 @@ int opp_submit(opp_handle_t h, const opp_batch_t *b, int *ticket)
         set_err(&h->err, "opp_submit: bad memory kind or layout");
         return OPP_ERR_INVALID;
     }
-    CU(cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
     const int si = h->next_slot;
     Slot &s = h->slots[si];
     if (s.busy) {
@@ -666,7 +685,7 @@ int opp_wait(opp_handle_t h, int ticket)
         return OPP_ERR_INVALID;
     }
     Slot &s = *sp;
-    CU(cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
     cudaError_t e = cudaEventSynchronize(s.ev_done);
     s.busy = false;
     if (e != cudaSuccess) {
@@ -752,7 +771,7 @@ int opp_debug_fetch(opp_handle_t h, int ticket, int what, int frame, int index, 
     Slot *sp = slot_of(h, ticket);
     if (!sp || sp->busy || frame < 0 || frame >= sp->n_frames) return -1;
     Slot &s = *sp;
-    cudaSetDevice(h->device);
+    DeviceGuard guard_(h->device);
     const int capP = h->cfg.max_peaks_per_part, capH = h->cfg.max_humans;
     auto d2h = [&](void *d, const void *src, size_t bytes) { return cudaMemcpy(d, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess; };
     switch (what) {
@@ -788,7 +807,7 @@ int opp_debug_fetch(opp_handle_t h, int ticket, int what, int frame, int index, 
 int opp_resize_device(opp_handle_t h, const float *src, int channels, int n_frames, float *dst, int dst_layout, void *stream)
 {
     if (!h || !src || !dst || channels < 1 || n_frames < 1) return OPP_ERR_INVALID;
-    CU(cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
     K1Params k1{};
     k1.g = h->g, k1.src = src, k1.dst = dst, k1.C = channels, k1.n = n_frames, k1.layout = dst_layout;
     CU(launch_k1(k1, stream ? (cudaStream_t)stream : h->slots[0].stream));
@@ -818,7 +837,7 @@ int opp_resize_pair_device(opp_handle_t h, const float *conf, const float *paf, 
                            void *stream)
 {
     if (!h || !conf || !paf || !conf_up || !paf_up || n_frames < 1) return OPP_ERR_INVALID;
-    CU(cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
     K1Params k1{};
     k1.g = h->g, k1.n = n_frames, k1.layout = dst_layout;
     k1.src = conf, k1.dst = conf_up, k1.C = OPP_N_HEAT;
@@ -836,7 +855,7 @@ int opp_peaks_device(opp_handle_t h, const float *conf, const float *paf, int n_
         return OPP_ERR_INVALID;
     }
     if ((conf_up || paf_up) && !(conf_up && paf_up && paf)) return OPP_ERR_INVALID;
-    CU(cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
     Slot &s = h->slots[0];
     if (s.busy) return OPP_ERR_BUSY;
     cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
@@ -852,7 +871,7 @@ int opp_peaks_device(opp_handle_t h, const float *conf, const float *paf, int n_
 int opp_timer_start(opp_handle_t h)
 {
     if (!h) return OPP_ERR_INVALID;
-    CU(cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
     for (auto &s : h->slots) {
         CU(cudaEventRecord(s.ev_join, s.stream));
         CU(cudaStreamWaitEvent(h->timer_stream, s.ev_join, 0));
@@ -866,7 +885,7 @@ int opp_timer_start(opp_handle_t h)
 float opp_timer_stop(opp_handle_t h)
 {
     if (!h) return -1.f;
-    cudaSetDevice(h->device);
+    DeviceGuard guard_(h->device);
     for (auto &s : h->slots) {
         if (cudaEventRecord(s.ev_join, s.stream) != cudaSuccess) return -1.f;
         if (cudaStreamWaitEvent(h->timer_stream, s.ev_join, 0) != cudaSuccess) return -1.f;

@@ -1527,14 +1527,26 @@ template <typename Kern> static cudaError_t allow_big_smem(Kern kern, int *dyn_l
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, *dyn_limit);
 }
 
+// The attribute is per kernel AND per device (a process may hold handles on several GPUs): each
+// launcher caches the limit per device ordinal.
+#define OPP_MAX_DEVICES 64
+#define BIG_SMEM_LIMIT(kern, out)                                                   \
+    do {                                                                            \
+        static int cache_[OPP_MAX_DEVICES];                                         \
+        int dev_ = 0;                                                               \
+        if (cudaGetDevice(&dev_) != cudaSuccess || dev_ < 0 || dev_ >= OPP_MAX_DEVICES) dev_ = 0; \
+        if (!cache_[dev_]) {                                                        \
+            cudaError_t e_ = allow_big_smem(kern, &cache_[dev_]);                   \
+            if (e_ != cudaSuccess) return e_;                                       \
+        }                                                                           \
+        out = cache_[dev_];                                                         \
+    } while (0)
+
 template <int S, int R, bool STORE>
 static cudaError_t launch_k2_fast_t(const K2Params &p, int n_frames, size_t smem, cudaStream_t st)
 {
-    static int dyn_limit = 0;
-    if (!dyn_limit) {
-        cudaError_t e = allow_big_smem(k2_peaks_fast<S, R, STORE>, &dyn_limit);
-        if (e != cudaSuccess) return e;
-    }
+    int dyn_limit = 0;
+    BIG_SMEM_LIMIT((k2_peaks_fast<S, R, STORE>), dyn_limit);
     if (smem > (size_t)dyn_limit) return cudaErrorInvalidValue;
     dim3 grid(p.nxs * p.nys, STORE ? OPP_N_HEAT : OPP_N_PARTS, n_frames);
     const int groups = (S * p.tw + 61) / 62;
@@ -1588,11 +1600,8 @@ cudaError_t launch_k2_generic(const K2Params &p, int n_frames, cudaStream_t st)
     const int IW = G_TX + 2 + 2 * R, IH = G_TY + 2 + 2 * R, TW = G_TX + 2;
     size_t smem = ((size_t)IH * IW + (size_t)IH * TW + (size_t)(G_TY + 2) * TW) * sizeof(float);
     if ((size_t)OPP_N_PARTS * p.capP * sizeof(int) > smem) smem = (size_t)OPP_N_PARTS * p.capP * sizeof(int);
-    static int dyn_limit = 0;
-    if (!dyn_limit) {
-        cudaError_t e = allow_big_smem(k2_peaks_generic, &dyn_limit);
-        if (e != cudaSuccess) return e;
-    }
+    int dyn_limit = 0;
+    BIG_SMEM_LIMIT(k2_peaks_generic, dyn_limit);
     if (smem > (size_t)dyn_limit) return cudaErrorInvalidValue;
     const int tiles = ((p.g.W + G_TX - 1) / G_TX) * ((p.g.H + G_TY - 1) / G_TY);
     dim3 grid(tiles, OPP_N_PARTS, n_frames);
@@ -1602,11 +1611,8 @@ cudaError_t launch_k2_generic(const K2Params &p, int n_frames, cudaStream_t st)
 
 cudaError_t launch_k3(const K3Params &p, int n_frames, size_t smem, cudaStream_t st)
 {
-    static int dyn_limit = 0;
-    if (!dyn_limit) {
-        cudaError_t e = allow_big_smem(k3_limbs, &dyn_limit);
-        if (e != cudaSuccess) return e;
-    }
+    int dyn_limit = 0;
+    BIG_SMEM_LIMIT(k3_limbs, dyn_limit);
     if (smem > (size_t)dyn_limit) return cudaErrorInvalidValue;
     dim3 grid(OPP_N_PAIRS, n_frames);
     k3_limbs<<<grid, OPP_THREADS, smem, st>>>(p);
@@ -1628,9 +1634,9 @@ cudaError_t launch_k1(const K1Params &p, cudaStream_t st)
         const size_t smem = ((size_t)g.W * Cmax + (size_t)Cmax * g.w) * sizeof(float);
         const bool ok16 = (((size_t)g.W * p.C * 4) & 15) == 0 && (p.C2 == 0 || (((size_t)g.W * p.C2 * 4) & 15) == 0) &&
                           ((reinterpret_cast<uintptr_t>(p.dst) | reinterpret_cast<uintptr_t>(p.dst2)) & 15) == 0;
-        static int dyn_limit = 0;
-        if (!dyn_limit && allow_big_smem(k1_replicate_hwc<8>, &dyn_limit) != cudaSuccess) dyn_limit = -1;
-        if (ok16 && dyn_limit > 0 && smem <= (size_t)dyn_limit) {
+        int dyn_limit = 0;
+        BIG_SMEM_LIMIT(k1_replicate_hwc<8>, dyn_limit);
+        if (ok16 && smem <= (size_t)dyn_limit) {
             dim3 grid(g.h, p.C2 ? 2 : 1, p.n);
             k1_replicate_hwc<8><<<grid, OPP_THREADS, smem, st>>>(p);
             return cudaGetLastError();

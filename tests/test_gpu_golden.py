@@ -203,3 +203,33 @@ def test_pageable_host_buffers_and_slot_reuse(mods):
             eng.submit(conf[:2], paf[:2])
         finally:
             eng.wait(t1), eng.wait(t2)
+
+
+def test_two_devices_in_one_process(mods):
+    """Handles on different GPUs of one process (kernel attributes are per device)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    Engine, capi, H = mods
+    conf, paf = synth.render_batch(2, n_people=3, seed0=970)
+    e0, e1 = Engine(46, 54, max_batch=2, device=0), Engine(46, 54, max_batch=2, device=1)
+    r0, r1 = e0.process(conf, paf), e1.process(conf, paf)
+    assert e0.device == 0 and e1.device == 1
+    assert np.array_equal(r0[1], r1[1])
+    for f in range(2):
+        assert H.humans_equal(r0[0][f, :r0[1][f]], r1[0][f, :r1[1][f]]) is None
+
+
+def test_calls_leave_the_callers_current_device_alone(mods):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    Engine, capi, H = mods
+    torch.cuda.set_device(0)
+    conf, paf = synth.render_batch(1, n_people=2, seed0=980)
+    e1 = Engine(46, 54, max_batch=1, device=1)
+    assert torch.cuda.current_device() == 0
+    e1.process(conf, paf)
+    assert torch.cuda.current_device() == 0
+    e1.close()
+    assert torch.cuda.current_device() == 0
