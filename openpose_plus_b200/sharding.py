@@ -46,3 +46,40 @@ def process_stream(engine, conf, paf, rank=0, world=1, batch=None, group=None, *
     for t in inflight:
         engine.wait(t)
     return gather_results((humans, counts, flags), rank, world, group)
+
+
+def process_stream_multi(engines, conf, paf, batch=None, **kw):
+    """One process, several GPUs (BASELINE.json configs[4]: a stream sharded over the GPUs of one box,
+    per-GPU streams, host gather).  `engines` = one Engine per device; the stream is cut into contiguous
+    shards, batches are submitted round-robin so every GPU keeps all its slots in flight, and the results
+    come back in frame order.  conf/paf are host arrays (pinned for full PCIe rate)."""
+    from . import _capi as capi
+    n, world = int(conf.shape[0]), len(engines)
+    max_h = engines[0].max_humans
+    humans = np.zeros((n, max_h), capi.HUMAN_DT)
+    counts = np.zeros(n, np.int32)
+    flags = np.zeros(n, np.int32)
+    cursors, inflight = [], []
+    for r, eng in enumerate(engines):
+        lo, hi = shard_range(n, r, world)
+        cursors.append([lo, hi])
+        inflight.append([])
+    pending = True
+    while pending:
+        pending = False
+        for r, eng in enumerate(engines):
+            lo, hi = cursors[r]
+            if lo >= hi:
+                continue
+            pending = True
+            b = batch or eng.max_batch
+            if len(inflight[r]) == int(eng.cfg.n_slots):
+                eng.wait(inflight[r].pop(0))
+            e = min(lo + b, hi)
+            out = (humans[lo:e], counts[lo:e], flags[lo:e])
+            inflight[r].append(eng.submit(conf[lo:e], paf[lo:e], out=out, **kw))
+            cursors[r][0] = e
+    for r, eng in enumerate(engines):
+        for t in inflight[r]:
+            eng.wait(t)
+    return humans, counts, flags

@@ -233,3 +233,22 @@ def test_calls_leave_the_callers_current_device_alone(mods):
     assert torch.cuda.current_device() == 0
     e1.close()
     assert torch.cuda.current_device() == 0
+
+
+def test_single_process_multi_gpu_stream(mods):
+    """configs[4] in one process: the stream sharded over every visible GPU equals the single-GPU result."""
+    import torch
+    from openpose_plus_b200.sharding import process_stream, process_stream_multi
+    Engine, capi, H = mods
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs two GPUs")
+    base_c, base_p = synth.render_batch(8, n_people=4, seed0=990)
+    idx = np.arange(1000) % 8
+    conf, paf = base_c[idx], base_p[idx]
+    engines = [Engine(46, 54, max_batch=32, device=d) for d in range(ndev)]
+    humans, counts, flags = process_stream_multi(engines, conf, paf)
+    h1, c1, f1 = process_stream(engines[0], conf, paf)
+    assert np.array_equal(counts, c1) and np.array_equal(flags, f1)
+    for f in range(0, 1000, 37):
+        assert H.humans_equal(humans[f, :counts[f]], h1[f, :c1[f]]) is None
