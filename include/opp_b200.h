@@ -168,6 +168,11 @@ int opp_peaks_device(opp_handle_t h, const float *conf, const float *paf, int n_
 int opp_timer_start(opp_handle_t h);
 float opp_timer_stop(opp_handle_t h);
 
+/* Skeleton overlay of one human on an interleaved 8-bit image (1..4 channels, first three written as
+ * R,G,B of the reference's palette): the role of draw_human (examples/vis.cpp:56-81) without OpenCV.
+ * row_stride_bytes = 0 means width * channels.  Host code; needs no GPU and no handle. */
+int opp_draw_human(uint8_t *image, int height, int width, int channels, ptrdiff_t row_stride_bytes, const opp_human_t *human, int thickness);
+
 const char *opp_last_error(opp_handle_t h);
 const char *opp_version(void);
 

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libopp_b200.so")
-SOURCES = ["opp_kernels.cu", "opp_capi.cu", "paf_processor.cpp"]
+SOURCES = ["opp_kernels.cu", "opp_capi.cu", "paf_processor.cpp", "vis.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: every float operation that decides an output must round exactly like the
 # reference's strict-IEEE scalar code; nothing on this path wants a fused multiply-add.

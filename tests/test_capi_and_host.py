@@ -167,3 +167,49 @@ def test_draw_humans_marks_parts_and_limbs():
     assert tuple(img[300, 300]) == CocoColors[10]          # isolated part: its dot
     assert tuple(img[65, 125]) == CocoColors[0]            # midpoint of limb 0 (neck - right shoulder)
     assert img[200, 50].sum() == 0
+
+
+def test_c_draw_human_overlay_and_cpp_header():
+    """opp_draw_human (host code in the C-ABI library, the role of examples/vis.cpp:56-81): limb lines, part
+    dots, clipping at the border, argument errors; and <openpose-plus/vis.h> compiles against it."""
+    import ctypes as C
+    L = capi.lib()
+    rec = np.zeros(1, capi.HUMAN_DT)
+    rec[0]["parts"][1] = (1, [0, 0, 0], 100.9, 50.2, 0.9)
+    rec[0]["parts"][2] = (1, [0, 0, 0], 150.0, 80.0, 0.9)
+    rec[0]["parts"][10] = (1, [0, 0, 0], 431.0, 367.0, 0.9)      # in the corner: must clip, not write outside
+    guard = np.zeros((370, 432, 3), np.uint8)
+    img = guard[1:369]
+    assert L.opp_draw_human(img.ctypes.data, 368, 432, 3, 0, rec.ctypes.data, 2) == capi.OK
+    from openpose_plus_b200.common import CocoColors
+    assert tuple(img[367, 431]) == CocoColors[10] and tuple(img[80, 150]) == CocoColors[2] and tuple(img[50, 100]) == CocoColors[1]
+    assert tuple(img[65, 125]) == CocoColors[0]                  # midpoint of limb 0
+    assert img[200, 50].sum() == 0 and guard[0].sum() == 0 and guard[369].sum() == 0
+    n_painted = int((img.sum(axis=2) > 0).sum())
+    assert 150 < n_painted < 400                                 # a 2-px line of ~58 px and three small dots
+    assert L.opp_draw_human(None, 368, 432, 3, 0, rec.ctypes.data, 2) == capi.ERR_INVALID
+    assert L.opp_draw_human(img.ctypes.data, 368, 432, 5, 0, rec.ctypes.data, 2) == capi.ERR_INVALID
+    src = r'''
+#include <string>
+#include <vector>
+#include <openpose-plus.h>
+#include <openpose-plus/vis.h>
+int main() {
+    std::vector<uint8_t> img(64 * 64 * 3, 0);
+    human_t h;
+    h.parts[0].has_value = true, h.parts[0].x = 10, h.parts[0].y = 12;
+    h.parts[1].has_value = true, h.parts[1].x = 40, h.parts[1].y = 50;
+    draw_human(img.data(), 64, 64, 3, h);
+    return img[(12 * 64 + 10) * 3] == 255 && img[(31 * 64 + 25) * 3 + 2] == 255 ? 0 : 1;   // nose dot red, limb 12 blue
+}
+'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        cpp, exe = os.path.join(d, "t.cpp"), os.path.join(d, "t")
+        open(cpp, "w").write(src)
+        libdir = os.path.join(ROOT, "openpose_plus_b200")
+        cmd = ["g++", "-std=c++14", "-I", os.path.join(ROOT, "include"), cpp, "-o", exe, "-L", libdir, "-l:libopp_b200.so",
+               "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert subprocess.run([exe]).returncode == 0
