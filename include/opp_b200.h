@@ -45,6 +45,18 @@ enum {
     OPP_FLAG_UB_ERASE_PAST_END = 32 /* reference erases at a stale id >= size() (src/paf.cpp:231); restated as libstdc++ 13 behaves */
 };
 
+/* Which of the reference's two post-processing semantics a handle reproduces.
+ *  OPP_VARIANT_CPP    -- the C++ path, the parity target: cv::GaussianBlur(k, sigma 3) with REFLECT_101 borders
+ *                        (src/post-process.h:51-72) and getHumans with its stored-id indexing (src/paf.cpp:177-262).
+ *  OPP_VARIANT_PYTHON -- the Python path (openpose_plus/inference/post_process.py:13-37,82-106): separable form of
+ *                        the CDF-derived kernel of _gauss_kernel(k, 3.0) with tf 'SAME' zero padding (the reference
+ *                        fixes k = 25), peaks where smoothed == 3x3 max-pool and smoothed > THRESH_HEAT, grouping as
+ *                        the external tf_pose `pafprocess` module does it (same scoring / sort / greedy matching as
+ *                        src/paf.cpp, humans indexed by position instead of stored id).  TensorFlow fixes no summation
+ *                        order and pafprocess is not vendored in the reference: parity of this variant is pinned only
+ *                        to this repo's restatement (oracle/), within float tolerance of a float64 2-D convolution. */
+enum { OPP_VARIANT_CPP = 0, OPP_VARIANT_PYTHON = 1 };
+
 enum { OPP_MEM_HOST = 0, OPP_MEM_DEVICE = 1 };
 enum { OPP_LAYOUT_CHW = 0, OPP_LAYOUT_HWC = 1 };
 
@@ -89,7 +101,8 @@ typedef struct {
     int32_t max_cands_per_limb;  /* default 1024 */
     int32_t max_humans;          /* default 128 (counts partial humans during assembly) */
     int32_t n_slots;             /* batches in flight (own stream + buffers each), default 3 */
-    int32_t reserved[3];
+    int32_t variant;             /* OPP_VARIANT_CPP (default) | OPP_VARIANT_PYTHON */
+    int32_t reserved[2];
 } opp_config_t;
 
 /* One batch of frames. */

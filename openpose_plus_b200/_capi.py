@@ -15,6 +15,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_BUSY = 0, 1, 2, 3, 4
 FLAG_PEAK_OVERFLOW, FLAG_CAND_OVERFLOW, FLAG_HUMAN_OVERFLOW = 1, 2, 4
 FLAG_UB_STALE_INDEX, FLAG_UB_PEAK_INDEX, FLAG_UB_ERASE_PAST_END = 8, 16, 32
 FLAG_OVERFLOW_MASK = 7
+VARIANT_CPP, VARIANT_PYTHON = 0, 1
 DBG_PEAKS, DBG_CONNS, DBG_PARTS, DBG_COUNTS = 0, 1, 2, 3
 
 PART_DT = np.dtype([("has_value", "u1"), ("pad", "u1", (3,)), ("x", "<f4"), ("y", "<f4"), ("score", "<f4")])
@@ -27,7 +28,7 @@ assert HUMAN_DT.itemsize == 292 and PEAK_DT.itemsize == 20 and CONN_DT.itemsize 
 class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "feat_h", "feat_w", "out_h", "out_w", "n_joins", "n_connections", "gauss_kernel_size", "max_batch",
-        "device", "max_peaks_per_part", "max_cands_per_limb", "max_humans", "n_slots")] + [("reserved", C.c_int32 * 3)]
+        "device", "max_peaks_per_part", "max_cands_per_limb", "max_humans", "n_slots", "variant")] + [("reserved", C.c_int32 * 2)]
 
 
 class Batch(C.Structure):

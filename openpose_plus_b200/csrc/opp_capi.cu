@@ -132,6 +132,24 @@ void gauss_taps(int k, double sigma, float *taps)
     for (int i = 0; i < k; ++i) taps[i] = (float)(t[i] * inv);
 }
 
+// Python-path variant: _gauss_kernel(ksize, nsig) of openpose_plus/inference/post_process.py:13-17 is
+// sqrt(outer(y, y)) / sum with y = diff(norm.cdf(linspace(-nsig - i/2, nsig + i/2, ksize + 1))), i = (2 nsig + 1) / ksize,
+// i.e. the outer product of g = sqrt(y) / sum(sqrt(y)) with itself: a separable filter.  Taps in double, rounded to float.
+void cdf_taps(int k, double nsig, float *taps)
+{
+    double e[OPP_MAX_KSIZE + 2], t[OPP_MAX_KSIZE + 1], sum = 0;
+    const double interval = (2 * nsig + 1.) / k, lo = -nsig - interval / 2., hi = nsig + interval / 2.;
+    for (int i = 0; i <= k; ++i) {
+        const double x = i == k ? hi : lo + (hi - lo) / k * i; // numpy.linspace: start + step * i, end point exact
+        e[i] = 0.5 * std::erfc(-x / std::sqrt(2.0));            // scipy.stats.norm.cdf
+    }
+    for (int i = 0; i < k; ++i) {
+        t[i] = std::sqrt(e[i + 1] - e[i]);
+        sum += t[i];
+    }
+    for (int i = 0; i < k; ++i) taps[i] = (float)(t[i] / sum);
+}
+
 // Area-mode coefficients of cv::resize(INTER_AREA) when up-sampling: s = floor(d*scale),
 // f = (float)((d+1) - (s+1)*inv_scale), f = f <= 0 ? 0 : f - floor(f); x additionally clamps at the
 // right edge.  Same statement as oracle/opp_oracle.c (validated against cv2 there).
@@ -360,6 +378,10 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
     if (c.max_humans <= 0) c.max_humans = 128;
     if (c.n_slots <= 0) c.n_slots = 3;
     const int k = c.gauss_kernel_size;
+    if (c.variant != OPP_VARIANT_CPP && c.variant != OPP_VARIANT_PYTHON) {
+        set_err(nullptr, "opp_create: variant must be OPP_VARIANT_CPP or OPP_VARIANT_PYTHON");
+        return OPP_ERR_INVALID;
+    }
     if (c.n_joins != OPP_N_HEAT || c.n_connections != OPP_N_PAIRS) {
         set_err(nullptr, "opp_create: n_joins and n_connections must be 19 (include/openpose-plus.hpp:63)");
         return OPP_ERR_INVALID;
@@ -407,7 +429,10 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
         OppGeom &g = h->g;
         g.h = c.feat_h, g.w = c.feat_w, g.H = c.out_h, g.W = c.out_w, g.K = k, g.R = k / 2;
         g.S = (c.out_h % c.feat_h == 0 && c.out_w % c.feat_w == 0 && c.out_h / c.feat_h == c.out_w / c.feat_w) ? c.out_h / c.feat_h : 0;
-        gauss_taps(k, 3.0, h->taps); // sigma fixed by the reference, src/post-process.h:54
+        if (c.variant == OPP_VARIANT_PYTHON)
+            cdf_taps(k, 3.0, h->taps); // nsig fixed by the reference, post_process.py:22
+        else
+            gauss_taps(k, 3.0, h->taps); // sigma fixed by the reference, src/post-process.h:54
         std::vector<int> xo, yo;
         std::vector<float> al, be;
         g.xmax = area_coeffs(g.w, g.W, true, xo, al);
@@ -421,7 +446,8 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
         CU(cudaMemcpy(h->d_alpha, al.data(), al.size() * sizeof(float), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(h->d_beta, be.data(), be.size() * sizeof(float), cudaMemcpyHostToDevice));
         g.xofs = h->d_xofs, g.yofs = h->d_yofs, g.alpha = h->d_alpha, g.beta = h->d_beta;
-        h->fast_k2 = k2_fast_supported(g);
+        // the fast kernel hard-wires cv::GaussianBlur's REFLECT_101 border and symmetric tap reuse
+        h->fast_k2 = k2_fast_supported(g) && c.variant == OPP_VARIANT_CPP;
         if (const char *e = getenv("OPP_FORCE_GENERIC")) {
             if (atoi(e)) h->fast_k2 = false;
         }
@@ -613,6 +639,7 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     k3.flags_out = k3_flags_out;
     k3.href_parts = s.d_href_parts, k3.stats = cnt_stats(h, s);
     k3.times = s.d_times;
+    k3.true_index = c.variant == OPP_VARIANT_PYTHON;
     k3.thr_vec = 0.05f, k3.thr_human = 0.4f; // THRESH_VECTOR_SCORE, THRESH_HUMAN_SCORE, src/paf.cpp:61,64
     CU(launch_k3(k3, n, h->k3_smem, st));
     h->launches += 1;
@@ -825,6 +852,7 @@ static int fill_k2(opp_handle_s *h, Slot &s, const float *conf, const float *con
     k2.flags = cnt_flags(h, s);
     std::memcpy(k2.taps, h->taps, sizeof k2.taps);
     k2.thresh = 0.05f; // THRESH_HEAT, src/paf.cpp:60
+    k2.border_zero = c.variant == OPP_VARIANT_PYTHON;
     k2.skip_thresh = h->k2_skip ? k2.thresh * (1.f - 1.f / 8192.f) : -INFINITY;
     if (h->fast_k2) {
         choose_k2_tiles(h, n, store, k2.tw, k2.th);

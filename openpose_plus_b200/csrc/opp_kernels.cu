@@ -806,7 +806,9 @@ __global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic(const K2Params p
         const int yy = y0 - 1 - R + t / IW, xx = x0 - 1 - R + t % IW;
         int ry = reflect101(yy, H), rx = reflect101(xx, W);
         ry = clip_idx(ry, H), rx = clip_idx(rx, W);
-        const float v = __ldcg(plane + (size_t)ry * W + rx);
+        float v = __ldcg(plane + (size_t)ry * W + rx);
+        // Python-path variant: 'SAME' zero padding of tf.nn.depthwise_conv2d (post_process.py:25-26)
+        if (p.border_zero && (yy < 0 || yy >= H || xx < 0 || xx >= W)) v = 0.f;
         in[t] = v;
         hot |= v > p.skip_thresh;
     }
@@ -822,9 +824,9 @@ __global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic(const K2Params p
         // reflect relative to the *centre* pixel: taps were staged by absolute reflected index, which
         // is what REFLECT_101 means for an in-image centre.
         float s;
-        if (K == 3) {
+        if (K == 3 && !p.border_zero) {
             s = __fadd_rn(__fmul_rn(q[R], p.taps[R]), __fmul_rn(__fadd_rn(q[R - 1], q[R + 1]), p.taps[R + 1]));
-        } else if (K == 5) {
+        } else if (K == 5 && !p.border_zero) {
             s = __fadd_rn(__fmul_rn(q[R], p.taps[R]), __fmul_rn(__fadd_rn(q[R - 1], q[R + 1]), p.taps[R + 1]));
             s = __fadd_rn(s, __fmul_rn(__fadd_rn(q[R - 2], q[R + 2]), p.taps[R + 2]));
         } else {
@@ -1108,7 +1110,9 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
                 unsigned m = __ballot_sync(0xffffffffu, t);
                 while (m && n_hits < 2) {
                     const int b = __ffs(m) - 1;
-                    const int id = hr[(base + b) * HR_WORDS + HR_ID];
+                    // src/paf.cpp:198 pushes the STORED id (stale after an erase); the Python path's pafprocess
+                    // keeps the position in the vector instead
+                    const int id = p.true_index ? base + b : hr[(base + b) * HR_WORDS + HR_ID];
                     if (n_hits == 0) hit0 = id; else hit1 = id;
                     ++n_hits;
                     m &= m - 1;

@@ -49,6 +49,7 @@ struct K2Params {
     float taps[OPP_MAX_KSIZE + 1];
     float thresh;
     unsigned long long *times; // optional [ctas][8] %globaltimer phase stamps (debug, single frame), may be null
+    int border_zero;   // generic kernel: taps outside the image read 0 (Python-path variant) instead of REFLECT_101
     float skip_thresh; // blocks whose 3x3 feature neighbourhood stays <= this cannot hold a peak; -inf disables the skip
 };
 
@@ -72,6 +73,7 @@ struct K3Params {
     // shared-memory carve-up (byte offsets)
     int off_paf, off_pk, off_cand, off_used, off_misc, off_href, off_score, off_conn, off_keep, off_owner;
     float thr_vec, thr_human;
+    int true_index;            // assembly indexes humans by position (pafprocess) instead of by stored id (src/paf.cpp:198,204)
     unsigned long long *times; // optional [n][19][12] %globaltimer stamps of the phases (debug), may be null
 };
 

@@ -28,7 +28,7 @@ def _is_device(a):
 
 class Engine:
     def __init__(self, feat_h, feat_w, out_h=None, out_w=None, gauss_kernel_size=17, max_batch=64, device=-1,
-                 max_peaks_per_part=128, max_cands_per_limb=1024, max_humans=128, n_slots=3):
+                 max_peaks_per_part=128, max_cands_per_limb=1024, max_humans=128, n_slots=3, variant=capi.VARIANT_CPP):
         self.L = capi.lib()
         out_h = 8 * feat_h if out_h is None else out_h
         out_w = 8 * feat_w if out_w is None else out_w
@@ -36,6 +36,7 @@ class Engine:
         self.L.opp_config_default(C.byref(cfg), feat_h, feat_w, out_h, out_w, gauss_kernel_size)
         cfg.max_batch, cfg.device = max_batch, device
         cfg.max_peaks_per_part, cfg.max_cands_per_limb, cfg.max_humans, cfg.n_slots = max_peaks_per_part, max_cands_per_limb, max_humans, n_slots
+        cfg.variant = variant
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.L.opp_create(C.byref(cfg), C.byref(self.h))

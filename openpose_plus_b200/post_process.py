@@ -72,9 +72,14 @@ def humans_from_records(records, height, width):
 
 class PostProcessor(object):
     def __init__(self, origin_size, feature_size, data_format='channels_last', gauss_kernel_size=17, device=-1,
-                 return_maps=True, maps_on_device=False, max_batch=1):
+                 return_maps=True, maps_on_device=False, max_batch=1, variant='cpp'):
         """origin_size: (height, width) the maps are up-sampled to; feature_size: (height', width') of
-        the feature maps; data_format: 'channels_last' ([h, w, C]) or 'channels_first' ([C, h, w])."""
+        the feature maps; data_format: 'channels_last' ([h, w, C]) or 'channels_first' ([C, h, w]).
+        variant: 'cpp' (default) = the semantics of the reference's C++ path, src/paf.cpp (the parity target);
+        'python' = the semantics of the reference's own Python graph (post_process.py:13-37: CDF-derived
+        kernel, zero padding -- pass gauss_kernel_size=25 for its fixed size -- and pafprocess-style grouping)."""
+        if variant not in ('cpp', 'python'):
+            raise ValueError("variant must be 'cpp' or 'python'")
         if data_format not in ('channels_last', 'channels_first'):
             raise ValueError('data_format must be channels_last or channels_first')
         self.data_format = data_format
@@ -82,7 +87,8 @@ class PostProcessor(object):
         self.feature_size = tuple(feature_size)
         self.return_maps, self.maps_on_device = return_maps, maps_on_device
         self.engine = Engine(feature_size[0], feature_size[1], origin_size[0], origin_size[1], gauss_kernel_size,
-                             max_batch=max_batch, device=device)
+                             max_batch=max_batch, device=device,
+                             variant=capi.VARIANT_PYTHON if variant == 'python' else capi.VARIANT_CPP)
         self._up = None
 
     def close(self):

@@ -48,38 +48,45 @@ def process_stream(engine, conf, paf, rank=0, world=1, batch=None, group=None, *
     return gather_results((humans, counts, flags), rank, world, group)
 
 
+def _run_shard(engine, conf, paf, lo, hi, batch, outs, kw):
+    """Keeps all slots of one engine busy over frames [lo, hi); results land in the caller's arrays."""
+    humans, counts, flags = outs
+    inflight = []
+    n_slots = int(engine.cfg.n_slots)
+    for s in range(lo, hi, batch):
+        e = min(s + batch, hi)
+        if len(inflight) == n_slots:
+            engine.wait(inflight.pop(0))
+        inflight.append(engine.submit(conf[s:e], paf[s:e], out=(humans[s:e], counts[s:e], flags[s:e]), **kw))
+    for t in inflight:
+        engine.wait(t)
+
+
 def process_stream_multi(engines, conf, paf, batch=None, **kw):
     """One process, several GPUs (BASELINE.json configs[4]: a stream sharded over the GPUs of one box,
     per-GPU streams, host gather).  `engines` = one Engine per device; the stream is cut into contiguous
-    shards, batches are submitted round-robin so every GPU keeps all its slots in flight, and the results
-    come back in frame order.  conf/paf are host arrays (pinned for full PCIe rate)."""
+    shards, one host thread per GPU keeps all slots of its engine in flight (the C-ABI calls release the
+    GIL and a blocking wait on one GPU never stalls submission to another), and the results come back in
+    frame order.  conf/paf are host arrays (pinned for full PCIe rate)."""
+    import threading
     from . import _capi as capi
     n, world = int(conf.shape[0]), len(engines)
-    max_h = engines[0].max_humans
-    humans = np.zeros((n, max_h), capi.HUMAN_DT)
-    counts = np.zeros(n, np.int32)
-    flags = np.zeros(n, np.int32)
-    cursors, inflight = [], []
-    for r, eng in enumerate(engines):
-        lo, hi = shard_range(n, r, world)
-        cursors.append([lo, hi])
-        inflight.append([])
-    pending = True
-    while pending:
-        pending = False
-        for r, eng in enumerate(engines):
-            lo, hi = cursors[r]
-            if lo >= hi:
-                continue
-            pending = True
-            b = batch or eng.max_batch
-            if len(inflight[r]) == int(eng.cfg.n_slots):
-                eng.wait(inflight[r].pop(0))
-            e = min(lo + b, hi)
-            out = (humans[lo:e], counts[lo:e], flags[lo:e])
-            inflight[r].append(eng.submit(conf[lo:e], paf[lo:e], out=out, **kw))
-            cursors[r][0] = e
-    for r, eng in enumerate(engines):
-        for t in inflight[r]:
-            eng.wait(t)
-    return humans, counts, flags
+    outs = (np.zeros((n, engines[0].max_humans), capi.HUMAN_DT), np.zeros(n, np.int32), np.zeros(n, np.int32))
+    errors, threads = [], []
+
+    def worker(r):
+        try:
+            lo, hi = shard_range(n, r, world)
+            _run_shard(engines[r], conf, paf, lo, hi, batch or engines[r].max_batch, outs, kw)
+        except BaseException as e:  # re-raised on the calling thread
+            errors.append(e)
+
+    for r in range(1, world):
+        threads.append(threading.Thread(target=worker, args=(r,)))
+        threads[-1].start()
+    worker(0)
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return outs

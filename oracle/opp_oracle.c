@@ -13,6 +13,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <stddef.h>
 #include <string.h>
 
 /* include/openpose-plus/coco.h:11-53 */
@@ -249,6 +250,55 @@ int orc_gauss_blur(const float *src, int H, int W, int ksize, double sigma, floa
     return 0;
 }
 
+/* Python-path variant.  openpose_plus/inference/post_process.py:13-17: _gauss_kernel(ksize, nsig) =
+ * sqrt(outer(y, y)) / sum, y = diff(norm.cdf(linspace(-nsig - i/2, nsig + i/2, ksize + 1))), i = (2 nsig + 1) / ksize.
+ * sqrt(outer(y, y)) = outer(sqrt y, sqrt y), so the 2-D filter is the outer product of g = sqrt(y) / sum(sqrt(y)). */
+int orc_cdf_kernel(int ksize, double nsig, float *taps)
+{
+    if (ksize < 1 || ksize > 255) return -1;
+    double e[257], t[256], sum = 0;
+    const double interval = (2 * nsig + 1.) / ksize, lo = -nsig - interval / 2., hi = nsig + interval / 2.;
+    for (int i = 0; i <= ksize; ++i) {
+        const double x = i == ksize ? hi : lo + (hi - lo) / ksize * i;
+        e[i] = 0.5 * erfc(-x / sqrt(2.0));
+    }
+    for (int i = 0; i < ksize; ++i) t[i] = sqrt(e[i + 1] - e[i]), sum += t[i];
+    for (int i = 0; i < ksize; ++i) taps[i] = (float)(t[i] / sum);
+    return 0;
+}
+
+/* tf.nn.depthwise_conv2d(..., padding='SAME') with that filter (post_process.py:20-26): pixels outside the image
+ * are zero.  TensorFlow fixes no summation order; this restatement (and the CUDA kernel) evaluates the separable
+ * form in float32: row pass left to right, column pass centre first then symmetric pairs outwards. */
+int orc_smooth_zero_pad(const float *src, int H, int W, int ksize, const float *k, float *dst)
+{
+    if (ksize < 1 || !(ksize & 1)) return -1;
+    const int r = ksize / 2;
+    float *row = (float *)calloc((size_t)(W + 2 * r), sizeof(float));
+    float *tmp = (float *)calloc((size_t)(H + 2 * r) * W, sizeof(float)); /* rows -r .. H+r-1, zero outside */
+    for (int y = 0; y < H; ++y) {
+        memcpy(row + r, src + (size_t)y * W, sizeof(float) * (size_t)W);
+        float *D = tmp + (size_t)(y + r) * W;
+        for (int x = 0; x < W; ++x) {
+            const float *p = row + x;
+            float s = k[0] * p[0];
+            for (int j = 1; j < ksize; ++j) s += k[j] * p[j];
+            D[x] = s;
+        }
+    }
+    for (int y = 0; y < H; ++y) {
+        float *D = dst + (size_t)y * W;
+        const float *c = tmp + (size_t)(y + r) * W;
+        for (int x = 0; x < W; ++x) {
+            float s = k[r] * c[x];
+            for (int j = 1; j <= r; ++j) s += k[r + j] * (c[x + (ptrdiff_t)j * W] + c[x - (ptrdiff_t)j * W]);
+            D[x] = s;
+        }
+    }
+    free(row), free(tmp);
+    return 0;
+}
+
 /* src/post-process.h:74-95 (CPU) == cuDNN 3x3/stride 1/pad 1 max pool for non-NaN input */
 void orc_max_pool_3x3(const float *src, int H, int W, float *dst)
 {
@@ -415,6 +465,7 @@ void orc_std_sort_desc(orc_cand_t *v, int n)
 /* ------------------------------------------------------------------------------------------- */
 struct orc_ctx {
     int h, w, H, W, ksize;
+    int variant; /* 0 = C++ path (src/paf.cpp, parity target), 1 = Python path (post_process.py + pafprocess) */
     resize_plan plan;
     float *rows;
     float *conf_up, *paf_up, *smoothed, *pooled;
@@ -451,6 +502,8 @@ orc_ctx *orc_create(int h, int w, int H, int W, int ksize)
     c->pooled = (float *)malloc(sizeof(float) * ORC_N_HEAT * px);
     return c;
 }
+
+void orc_set_variant(orc_ctx *c, int variant) { c->variant = variant; }
 
 void orc_destroy(orc_ctx *c)
 {
@@ -608,7 +661,8 @@ static void assemble(orc_ctx *c)
             for (int q = 0; q < c->n_hrefs; ++q) {
                 const orc_href_t *hr = &c->hrefs[q];
                 if (hr->parts[part1] == conn.cid1 || hr->parts[part2] == conn.cid2) {
-                    if (n_hits < 2) hits[n_hits] = hr->id;
+                    /* src/paf.cpp:198 records the STORED id; pafprocess (Python path) records the position */
+                    if (n_hits < 2) hits[n_hits] = c->variant == 1 ? q : hr->id;
                     n_hits++;
                 }
             }
@@ -717,7 +771,12 @@ static int run(orc_ctx *c, const float *conf, const float *paf, int lazy)
         for (int k = 0; k < ORC_N_PAF; ++k) resize_plane(&c->plan, paf + k * lp, c->paf_up + k * px, c->rows);
     /* src/post-process.h:160-174 (use_gpu=false branch; the cuDNN branch computes the same max) */
     for (int k = 0; k < ORC_N_HEAT; ++k) {
-        orc_gauss_blur(c->conf_up + k * px, c->H, c->W, c->ksize, 3.0, c->smoothed + k * px);
+        if (c->variant == 1) {
+            float taps[256];
+            orc_cdf_kernel(c->ksize, 3.0, taps);
+            orc_smooth_zero_pad(c->conf_up + k * px, c->H, c->W, c->ksize, taps, c->smoothed + k * px);
+        } else
+            orc_gauss_blur(c->conf_up + k * px, c->H, c->W, c->ksize, 3.0, c->smoothed + k * px);
         orc_max_pool_3x3(c->smoothed + k * px, c->H, c->W, c->pooled + k * px);
     }
     find_peaks(c);

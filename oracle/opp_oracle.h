@@ -73,6 +73,14 @@ typedef struct orc_ctx orc_ctx;
 
 orc_ctx *orc_create(int feat_h, int feat_w, int out_h, int out_w, int ksize);
 void orc_destroy(orc_ctx *);
+/* 0 (default) = the C++ path, src/paf.cpp -- the parity target, pinned against the reference build.
+ * 1 = the Python path's semantics (openpose_plus/inference/post_process.py:13-37 smoothing with the CDF-derived
+ *     kernel and zero padding; grouping as the external tf_pose pafprocess module: humans indexed by position).
+ *     PARITY UNPINNED for this variant: TensorFlow and pafprocess are absent from the reference tree and from this
+ *     image; the smoothing is checked against a float64 2-D convolution within tolerance only. */
+void orc_set_variant(orc_ctx *, int variant);
+int orc_cdf_kernel(int ksize, double nsig, float *taps);
+int orc_smooth_zero_pad(const float *src, int H, int W, int ksize, const float *taps, float *dst);
 /* Runs the whole path on one frame (conf [19,h,w], paf [38,h,w]); returns the number of humans. */
 int orc_run(orc_ctx *, const float *conf, const float *paf);
 /* Same, but skips materialising paf_up (samples are computed on demand, bit-identical). */

@@ -88,15 +88,21 @@ class Oracle:
             L.orc_std_sort_desc.argtypes = [C.c_void_p, C.c_int]
             L.orc_resize_coeffs.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]
             L.orc_resize_coeffs.restype = C.c_int
+            L.orc_set_variant.argtypes = [C.c_void_p, C.c_int]
+            L.orc_set_variant.restype = None
+            L.orc_cdf_kernel.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_float)]
+            L.orc_smooth_zero_pad.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
             cls._lib = L
         return cls._lib
 
-    def __init__(self, feat_h, feat_w, out_h, out_w, ksize=17):
+    def __init__(self, feat_h, feat_w, out_h, out_w, ksize=17, variant=0):
+        """variant 0 = the C++ path (src/paf.cpp, pinned); 1 = the Python path's semantics (unpinned, see opp_oracle.h)."""
         self.L = self.lib()
         self.h, self.w, self.H, self.W, self.ksize = feat_h, feat_w, out_h, out_w, ksize
         self.ctx = self.L.orc_create(feat_h, feat_w, out_h, out_w, ksize)
         if not self.ctx:
             raise ValueError("oracle: unsupported geometry/kernel size")
+        self.L.orc_set_variant(self.ctx, variant)
 
     def __del__(self):
         if getattr(self, "ctx", None):
@@ -140,6 +146,22 @@ class Oracle:
         if cls.lib().orc_gauss_kernel(k, sigma, t.ctypes.data_as(C.POINTER(C.c_float))):
             raise ValueError("bad kernel size")
         return t
+
+    @classmethod
+    def cdf_kernel(cls, k, nsig=3.0):
+        t = np.zeros(k, np.float32)
+        if cls.lib().orc_cdf_kernel(k, nsig, t.ctypes.data_as(C.POINTER(C.c_float))):
+            raise ValueError("bad kernel size")
+        return t
+
+    @classmethod
+    def smooth_zero_pad(cls, plane, taps):
+        plane, p = _f32(plane)
+        taps, pt = _f32(taps)
+        out = np.empty_like(plane)
+        if cls.lib().orc_smooth_zero_pad(p, plane.shape[0], plane.shape[1], len(taps), pt, out.ctypes.data_as(C.POINTER(C.c_float))):
+            raise ValueError("bad kernel size")
+        return out
 
     @classmethod
     def resize_area(cls, plane, H, W):

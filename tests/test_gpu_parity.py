@@ -112,3 +112,29 @@ def test_small_and_odd_geometries_on_the_fast_path(mods):
         orc = Oracle(fh, fw, fh * scale, fw * scale, k)
         H.run_and_check(eng, orc, conf, paf, "%dx%d x%d k=%d" % (fh, fw, scale, k))
         eng.close()
+
+
+def test_python_path_variant(mods):
+    """OPP_VARIANT_PYTHON: the semantics of the reference's Python graph (post_process.py:13-37: CDF-derived 25-tap
+    kernel, zero padding) with pafprocess-style grouping (humans indexed by position), bit-exact against this repo's
+    restatement of it (oracle variant 1; unpinned, see oracle/opp_oracle.h).  Crowded frames with the neck-nose limb
+    dropped give 30+ merges per frame, where the two grouping variants differ."""
+    Engine, Oracle, H = mods
+    from openpose_plus_b200 import _capi as capi
+    conf, paf = synth.render_batch(4, n_people=5, seed0=100)
+    eng, orc = Engine(46, 54, gauss_kernel_size=25, max_batch=6, max_humans=256, variant=capi.VARIANT_PYTHON), Oracle(46, 54, 368, 432, 25, variant=1)
+    H.run_and_check(eng, orc, conf, paf, "python variant")
+    fr = [synth.render_frame(200 + i, n_people=30 + 2 * i, drop_limbs=(12,) if i % 2 else ()) for i in range(6)]
+    conf, paf = np.stack([f[0] for f in fr]), np.stack([f[1] for f in fr])
+    humans, counts, flags = H.run_and_check(eng, orc, conf, paf, "python variant, crowded")
+    assert not (flags & (capi.FLAG_UB_STALE_INDEX | capi.FLAG_UB_ERASE_PAST_END)).any()   # positions are never stale
+    # and it is a different result from the C++ path's on the same maps
+    cpp = Engine(46, 54, gauss_kernel_size=25, max_batch=6, max_humans=256)
+    _, counts_cpp, _ = cpp.process(conf, paf)
+    assert not np.array_equal(counts, counts_cpp)
+    # other kernel sizes / geometries, maps touching the border (zero padding matters there)
+    conf, paf = synth.render_batch(2, n_people=8, seed0=410)
+    conf[:, :18, :3, :] = np.maximum(conf[:, :18, :3, :], 0.3 * np.random.default_rng(5).random((2, 18, 3, 54), dtype=np.float32))
+    for (oh, ow, k) in [(368, 432, 17), (300, 400, 25), (46 * 4, 54 * 4, 9), (92, 108, 3)]:
+        eng, orc = Engine(46, 54, oh, ow, gauss_kernel_size=k, max_batch=2, max_peaks_per_part=512, variant=capi.VARIANT_PYTHON), Oracle(46, 54, oh, ow, k, variant=1)
+        H.run_and_check(eng, orc, conf, paf, "python variant %dx%d k=%d" % (oh, ow, k))

@@ -96,3 +96,46 @@ def test_oracle_matches_live_reference_on_fresh_frames():
         conf, paf = synth.render_frame(seed, people, **kw)
         o = orc.run(conf, paf)
         assert helpers.humans_equal(o["humans"], ref.run(conf, paf)) is None, seed
+
+
+def test_python_path_kernel_and_zero_padded_smoothing():
+    """Oracle variant 1 (the reference's Python graph, post_process.py:13-26): the separable taps reproduce
+    _gauss_kernel's 2-D filter and the float32 separable zero-padded smoothing stays within float tolerance of a
+    float64 2-D convolution (TensorFlow fixes no summation order: tolerance, not bits)."""
+    st = pytest.importorskip("scipy.stats")
+    sig = pytest.importorskip("scipy.signal")
+
+    def gauss_kernel(ksize, nsig):                  # post_process.py:13-17, restated
+        interval = (2 * nsig + 1.) / ksize
+        x = np.linspace(-nsig - interval / 2., nsig + interval / 2., ksize + 1)
+        y = np.diff(st.norm.cdf(x))
+        k = np.sqrt(np.outer(y, y))
+        return k / k.sum()
+
+    for k in (25, 17, 9, 3, 1):
+        t = Oracle.cdf_kernel(k).astype(np.float64)
+        g2 = gauss_kernel(k, 3.0)
+        assert np.abs(np.outer(t, t) - g2).max() <= 2e-7 * g2.max()
+        assert abs(t.sum() - 1.0) < 1e-6 and (t > 0).all()
+    rng = np.random.default_rng(0)
+    img = rng.random((97, 131)).astype(np.float32)
+    got = Oracle.smooth_zero_pad(img, Oracle.cdf_kernel(25))
+    want = sig.convolve2d(img.astype(np.float64), gauss_kernel(25, 3.0), mode="same", boundary="fill")
+    assert np.abs(got - want).max() < 1e-6
+    # zero padding: a constant image fades towards the border (REFLECT_101 would keep it constant)
+    flat = Oracle.smooth_zero_pad(np.ones((64, 64), np.float32), Oracle.cdf_kernel(25))
+    assert abs(flat[32, 32] - 1) < 1e-6 and flat[0, 0] < 0.4 and flat[0, 32] < 0.7
+
+
+def test_python_path_grouping_indexes_by_position():
+    """Variant 1 groups like pafprocess (position in the vector); variant 0 like src/paf.cpp (stored id, stale after an
+    erase).  They agree until the first merge and may differ after it; variant 1 never raises the stale-index flags."""
+    from openpose_plus_b200 import synth
+    c, p = synth.render_frame(201, n_people=32, drop_limbs=(12,))
+    a, b = Oracle(46, 54, 368, 432, 17, variant=0).run(c, p), Oracle(46, 54, 368, 432, 17, variant=1).run(c, p)
+    assert a["n_merges"] > 0 and b["n_merges"] > 0
+    assert b["flags"] == 0
+    c, p = synth.render_frame(3, n_people=5)
+    o0, o1 = Oracle(46, 54, 368, 432, 17), Oracle(46, 54, 368, 432, 17)
+    o1.L.orc_set_variant(o1.ctx, 0)
+    assert o0.run(c, p)["n_humans"] == o1.run(c, p)["n_humans"]
