@@ -87,6 +87,7 @@ struct opp_handle_s {
     bool fuse_resize = true;
     bool k2_skip = true;
     bool zero_copy_out = true;
+    bool pdl = true; // programmatic dependent launch on the latency path (OPP_NO_PDL=1 disables)
     int zero_copy_in_max = 0; // kernels reading pinned host maps in place: measured slower than staging them (kept for experiments)
     int ingest_max = 4;       // up to this many frames, pinned host maps are pulled in by one kernel instead of memset + 2 DMA copies
     cudaEvent_t trace_base = nullptr;
@@ -463,6 +464,7 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
         h->fuse_resize = getenv("OPP_NO_FUSE") == nullptr;
         h->k2_skip = getenv("OPP_K2_NOSKIP") == nullptr;
         h->zero_copy_out = getenv("OPP_NO_ZEROCOPY_OUT") == nullptr;
+        h->pdl = getenv("OPP_NO_PDL") == nullptr;
         if (const char *e = getenv("OPP_ZC_IN_MAX")) h->zero_copy_in_max = atoi(e);
         if (const char *e = getenv("OPP_INGEST_MAX")) h->ingest_max = atoi(e);
         CU(cudaStreamCreateWithFlags(&h->timer_stream, cudaStreamNonBlocking));
@@ -601,8 +603,12 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     if (fuse_up) k2.paf = paf, k2.up_conf = b.conf_up, k2.up_paf = b.paf_up;
     if (s.d_times && n == 1) k2.times = s.d_times + (size_t)c.max_batch * OPP_N_PAIRS * 12;
     int *d_flags = cnt_flags(h, s);
+    // Latency path (a few frames, nothing else recorded on the stream between the kernels): programmatic dependent
+    // launch lets the peak kernel be scheduled behind the ingest kernel and the limb kernel behind the peak kernel
+    // while their predecessor still runs; each waits (griddepcontrol.wait) before touching its results.
+    const bool pdl = h->pdl && n <= h->ingest_max && !h->trace && !forked;
     if (h->fast_k2) {
-        CU(launch_k2_fast(k2, n, st));
+        CU(launch_k2_fast(k2, n, st, pdl && ingest));
     } else {
         CU(launch_k2_generic(k2, n, st));
     }
@@ -641,7 +647,7 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     k3.times = s.d_times;
     k3.true_index = c.variant == OPP_VARIANT_PYTHON;
     k3.thr_vec = 0.05f, k3.thr_human = 0.4f; // THRESH_VECTOR_SCORE, THRESH_HUMAN_SCORE, src/paf.cpp:61,64
-    CU(launch_k3(k3, n, h->k3_smem, st));
+    CU(launch_k3(k3, n, h->k3_smem, st, pdl && h->fast_k2));
     h->launches += 1;
 
     if (h->trace) CU(cudaEventRecord(s.tr[4], st));

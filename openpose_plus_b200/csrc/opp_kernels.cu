@@ -43,6 +43,13 @@ __device__ __forceinline__ int reflect101(int p, int n)
     return p;
 }
 
+// Programmatic dependent launch (latency path, opp_capi.cu): a kernel launched with the programmatic-serialization
+// attribute may be scheduled while its predecessor still runs; it must not touch the predecessor's results before
+// pdl_wait() (which returns once the predecessor grid has completed and flushed).  pdl_trigger() in the predecessor
+// lets that early scheduling begin.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ int clip_idx(int v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); }
 
 // Asynchronous global -> shared staging (cp.async / LDGSTS): every thread queues all its pieces
@@ -306,6 +313,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k1_general(const K1Params p)
 __global__ void __launch_bounds__(OPP_THREADS) k0_ingest(const float *__restrict__ src0, float *__restrict__ dst0, size_t n0,
                                                          const float *__restrict__ src1, float *__restrict__ dst1, size_t n1, int *counters, int n_counters)
 {
+    pdl_trigger();
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
     for (size_t i = tid; i < (size_t)n_counters; i += nth) counters[i] = 0;
     const bool vec = ((reinterpret_cast<uintptr_t>(src0) | reinterpret_cast<uintptr_t>(src1) | reinterpret_cast<uintptr_t>(dst0) | reinterpret_cast<uintptr_t>(dst1)) & 15) == 0 &&
@@ -528,6 +536,8 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
     float *Rrow = smem + ((nr * w + 3) & ~3); // [nr][RW] row-pass result
     float *Pf = Rrow + ((nr * RW + 3) & ~3);  // [2][ib-ia][w] PAF feature rows of the tile (STORE only)
     const float *src = p.conf + ((size_t)frame * OPP_N_HEAT + part) * h * w + ilo * w;
+    pdl_wait();    // the maps (and the counters) may come from an ingest kernel still in flight
+    pdl_trigger(); // the limb kernel may be scheduled behind this grid; it waits for our completion itself
     stage_async(L, src, nr * w);
     if (STORE) {
         // staged up front: a load issued next to the store stream would queue behind it for microseconds
@@ -1057,6 +1067,23 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
     const bool all_conns = p.conns_in_smem != 0, pk_smem = p.score_in_smem != 0;
     if (threadIdx.x < OPP_N_PAIRS) s_nc[threadIdx.x] = __ldcg(p.n_conns + frame * OPP_N_PAIRS + threadIdx.x);
     if (threadIdx.x >= 32 && threadIdx.x < 40) s_state[threadIdx.x - 32] = 0;
+    // Forest form of the 17 tree limbs (see below): s_c1[limb][local index of a first-part peak] = flattened index of
+    // the limb's connection that starts at that peak (0xffff: none); s_in = bitmap over peak ids, set when the peak
+    // enters a human as the SECOND part of a tree-limb connection; s_lmb[t] = limb of flattened connection t.
+    unsigned short *s_c1 = reinterpret_cast<unsigned short *>(smem_raw + p.off_owner);                                     // [17][capP]
+    unsigned *s_in = reinterpret_cast<unsigned *>(smem_raw + p.off_owner + (((size_t)17 * capP * 2 + 15) & ~(size_t)15)); // [ceil(18 capP / 32)]
+    unsigned char *s_lmb = reinterpret_cast<unsigned char *>(s_in + (OPP_N_PARTS * capP + 31) / 32);                       // [19 capP]
+    __shared__ int s_pofs[OPP_N_PARTS + 1];
+    __shared__ int s_nwarp[OPP_THREADS / 32];
+    __shared__ unsigned char s_pa[OPP_N_PAIRS], s_pb[OPP_N_PAIRS]; // c_pair_a / c_pair_b for lane-divergent limb indices
+    if (threadIdx.x >= 96 && threadIdx.x < 96 + OPP_N_PAIRS) s_pa[threadIdx.x - 96] = (unsigned char)c_pair_a[threadIdx.x - 96], s_pb[threadIdx.x - 96] = (unsigned char)c_pair_b[threadIdx.x - 96];
+    const bool use_owner = p.owner_in_smem != 0 && all_conns;
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + OPP_N_PARTS + 1) s_pofs[threadIdx.x - 64] = __ldcg(pofs + threadIdx.x - 64);
+    if (use_owner) {
+        for (int t = threadIdx.x; t < 17 * capP; t += blockDim.x) s_c1[t] = 0xffff;
+        for (int t = threadIdx.x; t < (OPP_N_PARTS * capP + 31) / 32; t += blockDim.x) s_in[t] = 0u;
+        for (int t = threadIdx.x; t < capH * OPP_N_PARTS; t += blockDim.x) hr[(t / OPP_N_PARTS) * HR_WORDS + HR_PART + t % OPP_N_PARTS] = -1;
+    }
     if (pk_smem)
         for (int t = threadIdx.x; t < n_peaks; t += blockDim.x)
             s_pk[t] = make_int2(__ldcg(&peaks[t].x) | (__ldcg(&peaks[t].y) << 16), __float_as_int(__ldcg(&peaks[t].score)));
@@ -1076,14 +1103,15 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
             opp_conn_t c;
             c.cid1 = __ldcg(&g->cid1), c.cid2 = __ldcg(&g->cid2), c.score = __ldcg(&g->score);
             s_conn[t] = c;
+            if (use_owner) {
+                s_lmb[t] = (unsigned char)l;
+                if (l < 17) {
+                    const int la = c.cid1 - s_pofs[s_pa[l]];
+                    if (la >= 0 && la < capP) s_c1[l * capP + la] = (unsigned short)t;
+                    if (c.cid2 >= 0 && c.cid2 < OPP_N_PARTS * capP) atomicOr(&s_in[c.cid2 >> 5], 1u << (c.cid2 & 31));
+                }
+            }
         }
-    }
-    // owner[peak id] = index of the partial human holding that peak (tree limbs only, see do_tree_limb)
-    int *s_owner = reinterpret_cast<int *>(smem_raw + p.off_owner);
-    const bool use_owner = p.owner_in_smem != 0;
-    if (use_owner) {
-        for (int t = threadIdx.x; t < n_peaks; t += blockDim.x) s_owner[t] = -1;
-        for (int t = threadIdx.x; t < capH * OPP_N_PARTS; t += blockDim.x) hr[(t / OPP_N_PARTS) * HR_WORDS + HR_PART + t % OPP_N_PARTS] = -1;
     }
     __syncthreads();
 
@@ -1098,9 +1126,9 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
         return pk_smem ? __int_as_float(s_pk[id].y) : __ldcg(&peaks[id].score);
     };
     // one limb's connections, in acceptance order; warp 0 only
-    auto do_limb = [&](int pair_id, const opp_conn_t *cl, int nconn) {
+    auto do_limb = [&](int pair_id, const opp_conn_t *cl, int nconn, int kstart) {
         const int part1 = c_pair_a[pair_id], part2 = c_pair_b[pair_id];
-        for (int k = 0; k < nconn; ++k) {
+        for (int k = kstart; k < nconn; ++k) {
             const opp_conn_t conn = cl[k];
             // for (auto hr : human_refs) if (hr.touches(...)) hr_ids.push_back(hr.id)   src/paf.cpp:195-199
             int n_hits = 0, hit0 = -1, hit1 = -1;
@@ -1194,63 +1222,172 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
         }
     };
 
-    // The 17 tree limbs (pair_id <= 16) in parallel, one lane per connection.  Each of them brings a
-    // part that no human holds yet (its second part appears as a second part nowhere earlier and as a
-    // first part only later, include/openpose-plus/coco.h:33-53) and the greedy matching uses every
-    // peak at most once per limb, so a connection touches at most ONE human (the one holding cid1),
-    // connections of a limb never touch each other's humans, and nothing has been erased yet (stored id
-    // == index).  The sequential loop of src/paf.cpp:192-248 therefore reduces to: look the owner of
-    // cid1 up, extend it, or append a new human in connection order (prefix sum over the lanes).
-    auto do_tree_limb = [&](int pair_id, const opp_conn_t *cl, int nconn) {
+    // The 17 tree limbs (pair_id <= 16) as a forest, whole CTA.  Each of them brings a part that no human holds yet
+    // (its second part appears as a second part nowhere earlier and as a first part only later,
+    // include/openpose-plus/coco.h:33-53) and the greedy matching uses every peak at most once per limb, so a
+    // connection touches at most ONE human (the one holding cid1), a human takes at most one connection per limb, and
+    // nothing is erased (stored id == position).  The sequential loop of src/paf.cpp:192-248 therefore reduces to:
+    //   * a connection CREATES a human iff nobody holds its cid1 when its limb is reached: no connection of the parent
+    //     limb ends in cid1 (the neck, part 1, has no parent limb) and no earlier limb with the same first part (neck:
+    //     limbs 0, 1, 6, 9, 12; nose: limbs 13, 15) has a connection from the same peak;
+    //   * humans are numbered in (limb, connection) order of their creating connections (ordered compaction);
+    //   * a human then collects, limb after limb, the connection that starts at the peak it holds in that limb's first
+    //     part -- independent of every other human, so one thread per human walks the limbs with the reference's
+    //     score association ((s(cid2) + conn.score) added in limb order).
+    auto tree_limbs_forest = [&]() {
+        const int T = s_coff[17]; // connections of limbs 0..16, flattened in limb order
+        int created = 0;          // humans created so far (uniform over the CTA)
+        int *s_create = s_keep;   // [capH] creating connection of each human (s_keep is not in use yet)
+        const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        for (int base = 0; base < T; base += blockDim.x) {
+            const int t = base + threadIdx.x;
+            bool creator = false;
+            int l = 0;
+            opp_conn_t c;
+            c.cid1 = c.cid2 = -1, c.score = 0.f;
+            if (t < T) {
+                l = s_lmb[t], c = s_conn[t];
+                const int pa = s_pa[l], la = c.cid1 - s_pofs[pa];
+                bool owned = pa != 1 && c.cid1 >= 0 && c.cid1 < OPP_N_PARTS * capP && ((s_in[c.cid1 >> 5] >> (c.cid1 & 31)) & 1u);
+                if (la >= 0 && la < capP) {
+                    if (pa == 1) { // earlier limbs rooted at the neck
+                        if (l > 0) owned |= s_c1[0 * capP + la] != 0xffff;
+                        if (l > 1) owned |= s_c1[1 * capP + la] != 0xffff;
+                        if (l > 6) owned |= s_c1[6 * capP + la] != 0xffff;
+                        if (l > 9) owned |= s_c1[9 * capP + la] != 0xffff;
+                    } else if (l == 15) { // the nose roots limbs 13 and 15: a nose without a neck may already head limb 13's human
+                        owned |= s_c1[13 * capP + la] != 0xffff;
+                    }
+                }
+                creator = !owned;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, creator);
+            if (lane == 0) s_nwarp[warp] = __popc(m);
+            __syncthreads();
+            int before = created, total = 0;
+            for (int q = 0; q < nwarps; ++q) {
+                const int cq = s_nwarp[q];
+                if (q < warp) before += cq;
+                total += cq;
+            }
+            if (creator) {
+                const int pos = before + __popc(m & ((1u << lane) - 1));
+                if (pos < capH) { // part ids were preset to -1 by the whole CTA
+                    s_create[pos] = t;
+                    int *hq = hr + pos * HR_WORDS;
+                    hq[HR_ID] = pos;
+                    hq[HR_PART + s_pa[l]] = c.cid1, hq[HR_PART + s_pb[l]] = c.cid2;
+                }
+            }
+            created += total;
+            __syncthreads();
+        }
+        int tflags = 0;
+        if (created > capH) tflags |= OPP_FLAG_HUMAN_OVERFLOW, created = capH;
+        // Parts: a human's skeleton below its creating connection is at most three limbs deep (neck - shoulder - elbow -
+        // wrist, neck - hip - knee - ankle, neck - nose - eye - ear), so three rounds over (human, limb) settle every part.
+        // Limbs before the creating one find nothing: their first part is either not held or heads no connection there.
+        for (int round = 0; round < 3; ++round) {
+            for (int it = threadIdx.x; it < created * 17; it += blockDim.x) {
+                const int q = it / 17, l = it - q * 17;
+                int *hq = hr + q * HR_WORDS + HR_PART;
+                const int pa = s_pa[l], pb = s_pb[l];
+                const int held = hq[pa];
+                if (held < 0 || hq[pb] != -1) continue;
+                const int la = held - s_pofs[pa];
+                if (la < 0 || la >= capP) continue;
+                const int t = s_c1[l * capP + la];
+                if (t != 0xffff) hq[pb] = s_conn[t].cid2;
+            }
+            __syncthreads();
+        }
+        auto pscore = [&](int id) -> float {
+            if (id < 0 || id >= n_peaks) {
+                tflags |= OPP_FLAG_UB_PEAK_INDEX;
+                return 0.f;
+            }
+            return pk_smem ? __int_as_float(s_pk[id].y) : __ldcg(&peaks[id].score);
+        };
+        // Score and part count: the creating connection first (src/paf.cpp:243-244), then the human's connection of every
+        // later limb in limb order, each as (s(cid2) + conn.score) (:205-209).  The lookups of different limbs are
+        // independent now; only the additions are a chain.
+        for (int q = threadIdx.x; q < created; q += blockDim.x) {
+            int *hq = hr + q * HR_WORDS;
+            const int t0 = s_create[q], l0 = s_lmb[t0];
+            const opp_conn_t c0 = s_conn[t0];
+            float sc = __fadd_rn(__fadd_rn(pscore(c0.cid1), pscore(c0.cid2)), c0.score);
+            int np = 2;
+#pragma unroll
+            for (int l = 0; l < 17; ++l) {
+                const int held = hq[HR_PART + c_pair_a[l]];
+                const int la = held - s_pofs[c_pair_a[l]];
+                if (l == l0 || held < 0 || la < 0 || la >= capP) continue;
+                const int t = s_c1[l * capP + la];
+                if (t == 0xffff) continue;
+                const opp_conn_t c = s_conn[t];
+                sc = __fadd_rn(sc, __fadd_rn(pscore(c.cid2), c.score));
+                ++np;
+            }
+            hq[HR_NPARTS] = np, hq[HR_SCORE] = __float_as_int(sc);
+        }
+        flags |= __syncthreads_or(tflags);
+        n = created, hist_max = created;
+    };
+
+    // A virtual limb (17, 18) while nothing has been erased yet (stored id == position): 32 connections at a time,
+    // each lane finds the humans its connection touches.  A connection that touches nobody, or one human that already
+    // holds cid2, changes nothing; one human with that part still empty is extended -- and none of these can alter
+    // what another connection of the same limb touches (peaks are used once per limb).  Anything else (two humans:
+    // merge or overwrite; one human holding another peak there) is order dependent: from the first such connection
+    // on, the limb continues in the sequential form.  Returns the index to continue from (nconn: all done).
+    auto virtual_limb_prefix = [&](int pair_id, const opp_conn_t *cl, int nconn) -> int {
         const int part1 = c_pair_a[pair_id], part2 = c_pair_b[pair_id];
         for (int base = 0; base < nconn; base += 32) {
             const int k = base + lane;
             const bool on = k < nconn;
             opp_conn_t conn;
-            conn.cid1 = conn.cid2 = -1, conn.score = 0.f;
+            conn.cid1 = conn.cid2 = -2, conn.score = 0.f;
             if (on) conn = cl[k];
-            const bool id_ok = on && conn.cid1 >= 0 && conn.cid1 < n_peaks && conn.cid2 >= 0 && conn.cid2 < n_peaks;
-            const int q = id_ok ? s_owner[conn.cid1] : -1;
-            const bool fresh = on && q < 0;
-            const unsigned mnew = __ballot_sync(0xffffffffu, fresh);
-            const int slot = n + __popc(mnew & ((1u << lane) - 1));
-            if (on && q >= 0) {
-                int *h1 = hr + q * HR_WORDS;
-                if (h1[HR_PART + part2] != conn.cid2) {
-                    h1[HR_PART + part2] = conn.cid2;
-                    h1[HR_NPARTS] += 1;
-                    const float sc = __int_as_float(h1[HR_SCORE]);
-                    h1[HR_SCORE] = __float_as_int(__fadd_rn(sc, __fadd_rn(peak_score(conn.cid2), conn.score)));
-                    s_owner[conn.cid2] = q;
+            int nh = 0, h0 = 0;
+            if (on)
+                for (int q = 0; q < n; ++q) {
+                    const int *hq = hr + q * HR_WORDS + HR_PART;
+                    if (hq[part1] == conn.cid1 || hq[part2] == conn.cid2) {
+                        if (nh == 0) h0 = q;
+                        ++nh;
+                    }
                 }
-            } else if (fresh) {
-                if (slot >= capH) {
-                    flags |= OPP_FLAG_HUMAN_OVERFLOW;
-                } else {
-                    int *hn = hr + slot * HR_WORDS; // part ids were preset to -1 by the whole CTA
-                    hn[HR_PART + part1] = conn.cid1, hn[HR_PART + part2] = conn.cid2;
-                    hn[HR_ID] = slot, hn[HR_NPARTS] = 2;
-                    hn[HR_SCORE] = __float_as_int(__fadd_rn(__fadd_rn(peak_score(conn.cid1), peak_score(conn.cid2)), conn.score));
-                    if (id_ok) s_owner[conn.cid1] = slot, s_owner[conn.cid2] = slot;
-                }
+            const int cur = (on && nh == 1) ? hr[h0 * HR_WORDS + HR_PART + part2] : -2;
+            const bool noop = !on || nh == 0 || (nh == 1 && cur == conn.cid2);
+            const bool safe = on && nh == 1 && cur == -1;
+            const unsigned mh = __ballot_sync(0xffffffffu, !noop && !safe);
+            const int lim = mh ? __ffs(mh) - 1 : 32;
+            if (safe && lane < lim) {
+                int *h1 = hr + h0 * HR_WORDS;
+                h1[HR_PART + part2] = conn.cid2;
+                h1[HR_NPARTS] += 1;
+                const float sc = __int_as_float(h1[HR_SCORE]);
+                h1[HR_SCORE] = __float_as_int(__fadd_rn(sc, __fadd_rn(peak_score(conn.cid2), conn.score)));
             }
-            n = min(n + __popc(mnew), capH);
             __syncwarp();
+            if (mh) return base + lim;
         }
-        if (n > hist_max) hist_max = n;
+        return nconn;
     };
 
     if (all_conns) {
+        if (use_owner) {
+            tree_limbs_forest();
+            stamp(p, frame, 18, 10);
+        }
         if (threadIdx.x < 32)
-            for (int pair_id = 0; pair_id < OPP_N_PAIRS; ++pair_id) {
-                if (pair_id == 17) {
-                    for (int o = 16; o > 0; o >>= 1) flags |= __shfl_xor_sync(0xffffffffu, flags, o); // lanes diverged on UB / overflow flags
-                    stamp(p, frame, 18, 10);
+            for (int pair_id = use_owner ? 17 : 0; pair_id < OPP_N_PAIRS; ++pair_id) {
+                int k0 = 0;
+                if (pair_id >= 17 && merges == 0) {
+                    k0 = virtual_limb_prefix(pair_id, s_conn + s_coff[pair_id], s_nc[pair_id]);
+                    for (int o = 16; o > 0; o >>= 1) flags |= __shfl_xor_sync(0xffffffffu, flags, o); // lanes set UB flags on their own
                 }
-                if (use_owner && pair_id <= 16)
-                    do_tree_limb(pair_id, s_conn + s_coff[pair_id], s_nc[pair_id]);
-                else
-                    do_limb(pair_id, s_conn + s_coff[pair_id], s_nc[pair_id]);
+                do_limb(pair_id, s_conn + s_coff[pair_id], s_nc[pair_id], k0);
             }
     } else { // capacities too large to stage every limb at once: one limb at a time
         for (int pair_id = 0; pair_id < OPP_N_PAIRS; ++pair_id) {
@@ -1262,7 +1399,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
                 s_conn[t] = c;
             }
             __syncthreads();
-            if (threadIdx.x < 32) do_limb(pair_id, s_conn, s_nc[pair_id]);
+            if (threadIdx.x < 32) do_limb(pair_id, s_conn, s_nc[pair_id], 0);
         }
     }
 
@@ -1323,14 +1460,17 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
     }
 }
 
-__global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const K3Params p)
+// __grid_constant__: the parameter block is read through references (assemble_frame, the stamps); without the qualifier
+// taking its address makes every CTA copy it to local memory first
+__global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ K3Params p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int pair_id = blockIdx.x, frame = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int h = p.g.h, w = p.g.w, capP = p.capP, capC = p.capC;
-    const int pa = c_pair_a[pair_id], pb = c_pair_b[pair_id], cx = c_net_x[pair_id], cy = cx + 1;
+    const int pa = c_pair_a[pair_id], pb = c_pair_b[pair_id], cx = c_net_x[pair_id]; // the y channel is the next plane
     const int *pofs = p.part_ofs + frame * (OPP_N_PARTS + 1);
+    pdl_wait(); // peaks come from the peak kernel, which may still be running when this CTA is scheduled
     const int ofs_a = __ldcg(pofs + pa), na = __ldcg(pofs + pa + 1) - ofs_a;
     const int ofs_b = __ldcg(pofs + pb), nb = __ldcg(pofs + pb + 1) - ofs_b;
     const opp_peak_t *peaks = p.peaks + (size_t)frame * OPP_N_PARTS * capP;
@@ -1546,8 +1686,20 @@ template <typename Kern> static cudaError_t allow_big_smem(Kern kern, int *dyn_l
         out = cache_[dev_];                                                         \
     } while (0)
 
+// Launch with or without the programmatic-stream-serialization attribute (see pdl_wait above).
+template <typename P> static cudaError_t launch_ex(void (*kern)(const P), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, const P &p)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 template <int S, int R, bool STORE>
-static cudaError_t launch_k2_fast_t(const K2Params &p, int n_frames, size_t smem, cudaStream_t st)
+static cudaError_t launch_k2_fast_t(const K2Params &p, int n_frames, size_t smem, cudaStream_t st, bool pdl)
 {
     int dyn_limit = 0;
     BIG_SMEM_LIMIT((k2_peaks_fast<S, R, STORE>), dyn_limit);
@@ -1557,14 +1709,13 @@ static cudaError_t launch_k2_fast_t(const K2Params &p, int n_frames, size_t smem
     if (groups < 1 || groups > K2_FAST_MAX_WARPS || p.th + 4 > 64 || p.tw + 2 > 64) return cudaErrorInvalidValue; // 64-bit activity masks
     const int threads = 32 * groups;
     if (STORE && 4 * p.tw > threads) return cudaErrorInvalidValue; // two threads per 16-byte column of the tile
-    k2_peaks_fast<S, R, STORE><<<grid, threads, smem, st>>>(p);
-    return cudaGetLastError();
+    return launch_ex(k2_peaks_fast<S, R, STORE>, grid, dim3(threads), smem, st, pdl, p);
 }
 
 template <int S, int R>
-static cudaError_t launch_k2_fast_sr(const K2Params &p, int n_frames, size_t smem, cudaStream_t st)
+static cudaError_t launch_k2_fast_sr(const K2Params &p, int n_frames, size_t smem, cudaStream_t st, bool pdl)
 {
-    return p.up_conf ? launch_k2_fast_t<S, R, true>(p, n_frames, smem, st) : launch_k2_fast_t<S, R, false>(p, n_frames, smem, st);
+    return p.up_conf ? launch_k2_fast_t<S, R, true>(p, n_frames, smem, st, pdl) : launch_k2_fast_t<S, R, false>(p, n_frames, smem, st, pdl);
 }
 
 bool k2_fast_supported(const OppGeom &g)
@@ -1583,14 +1734,14 @@ size_t k2_fast_smem_bytes(const OppGeom &g, int tw, int th)
     return fl * sizeof(float);
 }
 
-cudaError_t launch_k2_fast(const K2Params &p, int n_frames, cudaStream_t st)
+cudaError_t launch_k2_fast(const K2Params &p, int n_frames, cudaStream_t st, bool pdl)
 {
     const size_t smem = k2_fast_smem_bytes(p.g, p.tw, p.th);
     size_t need = smem;
     if ((size_t)OPP_N_PARTS * p.capP * sizeof(int) > need) need = (size_t)OPP_N_PARTS * p.capP * sizeof(int);
     if (need > (size_t)g_max_smem) return cudaErrorInvalidValue;
 #define K2_CASE(S_, R_)                                                       \
-    if (p.g.S == S_ && p.g.R == R_) return launch_k2_fast_sr<S_, R_>(p, n_frames, need, st);
+    if (p.g.S == S_ && p.g.R == R_) return launch_k2_fast_sr<S_, R_>(p, n_frames, need, st, pdl);
     K2_CASE(8, 8) K2_CASE(8, 6) K2_CASE(8, 4)               // k = 17, 13, 9: the kernel sizes the reference's demos and scripts use
     K2_CASE(8, 7) K2_CASE(8, 5) K2_CASE(8, 3) K2_CASE(8, 2) K2_CASE(8, 1) K2_CASE(8, 0)
     K2_CASE(4, 4) K2_CASE(4, 3) K2_CASE(4, 2) K2_CASE(4, 1) K2_CASE(4, 0)
@@ -1613,14 +1764,13 @@ cudaError_t launch_k2_generic(const K2Params &p, int n_frames, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t launch_k3(const K3Params &p, int n_frames, size_t smem, cudaStream_t st)
+cudaError_t launch_k3(const K3Params &p, int n_frames, size_t smem, cudaStream_t st, bool pdl)
 {
     int dyn_limit = 0;
     BIG_SMEM_LIMIT(k3_limbs, dyn_limit);
     if (smem > (size_t)dyn_limit) return cudaErrorInvalidValue;
     dim3 grid(OPP_N_PAIRS, n_frames);
-    k3_limbs<<<grid, OPP_THREADS, smem, st>>>(p);
-    return cudaGetLastError();
+    return launch_ex(k3_limbs, grid, dim3(OPP_THREADS), smem, st, pdl, p);
 }
 
 static bool k1_fast_ok(const K1Params &p)
