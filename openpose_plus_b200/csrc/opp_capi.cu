@@ -51,6 +51,9 @@ struct Slot {
     // pinned results
     opp_human_t *h_humans = nullptr;
     int *h_n_humans = nullptr, *h_flags = nullptr;
+    int *h_done = nullptr;      // pinned completion word written by the assembly kernel (latency path)
+    int done_tag = 0;           // value that word takes when the batch in flight is complete; 0 = wait on the event
+    bool ms_pending = false;    // last_ms not read from the events yet
     // in-flight batch
     bool busy = false;
     bool direct_out = false; // results were written straight into the caller's pinned buffers
@@ -87,6 +90,8 @@ struct opp_handle_s {
     bool fuse_resize = true;
     bool k2_skip = true;
     bool zero_copy_out = true;
+    bool done_flag = true; // completion word in pinned memory on the latency path (OPP_NO_DONE_FLAG=1 disables)
+    int tag_seq = 0;
     bool pdl = true; // programmatic dependent launch on the latency path (OPP_NO_PDL=1 disables)
     int zero_copy_in_max = 0; // kernels reading pinned host maps in place: measured slower than staging them (kept for experiments)
     int ingest_max = 4;       // up to this many frames, pinned host maps are pulled in by one kernel instead of memset + 2 DMA copies
@@ -219,7 +224,7 @@ int free_slot(opp_handle_s *h, Slot &s)
     cudaFree(s.d_conf), cudaFree(s.d_paf), cudaFree(s.d_hwc), cudaFree(s.d_conf_up), cudaFree(s.d_counters);
     cudaFree(s.d_pk_key), cudaFree(s.d_peaks), cudaFree(s.d_part_ofs), cudaFree(s.d_conns), cudaFree(s.d_n_conns);
     cudaFree(s.d_cand), cudaFree(s.d_humans), cudaFree(s.d_n_humans), cudaFree(s.d_href_parts), cudaFree(s.d_times);
-    cudaFreeHost(s.h_humans), cudaFreeHost(s.h_n_humans), cudaFreeHost(s.h_flags);
+    cudaFreeHost(s.h_humans), cudaFreeHost(s.h_n_humans), cudaFreeHost(s.h_flags), cudaFreeHost(s.h_done);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
@@ -271,6 +276,8 @@ int alloc_slot(opp_handle_s *h, Slot &s)
     CU(cudaMallocHost(&s.h_humans, B * capH * sizeof(opp_human_t)));
     CU(cudaMallocHost(&s.h_n_humans, B * sizeof(int)));
     CU(cudaMallocHost(&s.h_flags, B * sizeof(int)));
+    CU(cudaMallocHost(&s.h_done, sizeof(int)));
+    *s.h_done = 0;
     return OPP_OK;
 }
 
@@ -279,10 +286,25 @@ int *cnt_k2(opp_handle_s *h, Slot &s) { return s.d_counters + (size_t)h->cfg.max
 int *cnt_k3(opp_handle_s *h, Slot &s) { return cnt_k2(h, s) + h->cfg.max_batch; }
 int *cnt_stats(opp_handle_s *h, Slot &s) { return cnt_k3(h, s) + h->cfg.max_batch; }
 int *cnt_flags(opp_handle_s *h, Slot &s) { return cnt_stats(h, s) + (size_t)h->cfg.max_batch * 4; }
+int *cnt_batch_done(opp_handle_s *h, Slot &s) { return cnt_flags(h, s) + h->cfg.max_batch; }
+
+// Pinned ranges handed out by opp_host_alloc: looked up without a driver call (cudaPointerGetAttributes costs about a
+// microsecond per pointer, and a batch carries up to five of them ahead of its first kernel launch).
+struct PinnedRange {
+    uintptr_t base, size, dev;
+};
+std::mutex g_pin_mu;
+std::vector<PinnedRange> g_pins;
 
 // Device-visible alias of a pinned (cudaMallocHost / cudaHostRegister) host pointer, or null.
 void *mapped_host(const void *p)
 {
+    {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        for (const PinnedRange &r : g_pins)
+            if (a >= r.base && a - r.base < r.size) return reinterpret_cast<void *>(r.dev + (a - r.base));
+    }
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
         cudaGetLastError();
@@ -345,12 +367,28 @@ void *opp_host_alloc(size_t bytes)
         set_err(nullptr, "cudaMallocHost(%zu) failed", bytes);
         return nullptr;
     }
+    void *d = nullptr;
+    if (cudaHostGetDevicePointer(&d, p, 0) == cudaSuccess && d) {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        g_pins.push_back({reinterpret_cast<uintptr_t>(p), bytes, reinterpret_cast<uintptr_t>(d)});
+    } else {
+        cudaGetLastError();
+    }
     return p;
 }
 
 void opp_host_free(void *p)
 {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        for (size_t i = 0; i < g_pins.size(); ++i)
+            if (g_pins[i].base == reinterpret_cast<uintptr_t>(p)) {
+                g_pins.erase(g_pins.begin() + i);
+                break;
+            }
+    }
+    cudaFreeHost(p);
 }
 
 void opp_destroy(opp_handle_t h)
@@ -459,12 +497,13 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
             set_err(&h->err, "opp_create: capacities need %zu bytes of shared memory (> %d)", h->k3_smem, h->max_smem);
             return OPP_ERR_INVALID;
         }
-        h->counters_ints = (size_t)c.max_batch * (OPP_N_PARTS + 1 + 1 + 4 + 1);
+        h->counters_ints = (size_t)c.max_batch * (OPP_N_PARTS + 1 + 1 + 4 + 1) + 1; // + frames assembled in this batch
         h->trace = getenv("OPP_TRACE") != nullptr;
         h->fuse_resize = getenv("OPP_NO_FUSE") == nullptr;
         h->k2_skip = getenv("OPP_K2_NOSKIP") == nullptr;
         h->zero_copy_out = getenv("OPP_NO_ZEROCOPY_OUT") == nullptr;
         h->pdl = getenv("OPP_NO_PDL") == nullptr;
+        h->done_flag = getenv("OPP_NO_DONE_FLAG") == nullptr;
         if (const char *e = getenv("OPP_ZC_IN_MAX")) h->zero_copy_in_max = atoi(e);
         if (const char *e = getenv("OPP_INGEST_MAX")) h->ingest_max = atoi(e);
         CU(cudaStreamCreateWithFlags(&h->timer_stream, cudaStreamNonBlocking));
@@ -606,7 +645,8 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     // Latency path (a few frames, nothing else recorded on the stream between the kernels): programmatic dependent
     // launch lets the peak kernel be scheduled behind the ingest kernel and the limb kernel behind the peak kernel
     // while their predecessor still runs; each waits (griddepcontrol.wait) before touching its results.
-    const bool pdl = h->pdl && n <= h->ingest_max && !h->trace && !forked;
+    const bool few = n <= h->ingest_max && !h->trace && !forked;
+    const bool pdl = h->pdl && few;
     if (h->fast_k2) {
         CU(launch_k2_fast(k2, n, st, pdl && ingest));
     } else {
@@ -645,6 +685,15 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     k3.flags_out = k3_flags_out;
     k3.href_parts = s.d_href_parts, k3.stats = cnt_stats(h, s);
     k3.times = s.d_times;
+    // Latency path with host-visible results: completion is announced through a pinned word (see K3Params::host_done)
+    s.done_tag = 0;
+    if (few && !dev_out && h->zero_copy_out && h->done_flag) {
+        s.done_tag = ++h->tag_seq;
+        if (s.done_tag == 0) s.done_tag = ++h->tag_seq;
+        k3.batch_done = cnt_batch_done(h, s), k3.host_done = (int *)mapped_host(s.h_done);
+        k3.done_tag = s.done_tag, k3.done_frames = n;
+        if (!k3.host_done) s.done_tag = 0;
+    }
     k3.true_index = c.variant == OPP_VARIANT_PYTHON;
     k3.thr_vec = 0.05f, k3.thr_human = 0.4f; // THRESH_VECTOR_SCORE, THRESH_HUMAN_SCORE, src/paf.cpp:61,64
     CU(launch_k3(k3, n, h->k3_smem, st, pdl && h->fast_k2));
@@ -719,13 +768,31 @@ int opp_wait(opp_handle_t h, int ticket)
     }
     Slot &s = *sp;
     DeviceGuard guard_(h->device);
-    cudaError_t e = cudaEventSynchronize(s.ev_done);
+    cudaError_t e = cudaSuccess;
+    bool retired = true;
+    if (s.done_tag) {
+        // spin on the completion word; look at the event now and then so that a failed launch cannot hang the caller
+        volatile int *f = s.h_done;
+        retired = false;
+        for (unsigned spins = 1; *f != s.done_tag; ++spins) {
+            if ((spins & 0x3fff) == 0) {
+                const cudaError_t q = cudaEventQuery(s.ev_done);
+                if (q != cudaErrorNotReady) {
+                    e = q, retired = true;
+                    break;
+                }
+            }
+        }
+    } else {
+        e = cudaEventSynchronize(s.ev_done);
+    }
     s.busy = false;
     if (e != cudaSuccess) {
         set_err(&h->err, "opp_wait: %s", cudaGetErrorString(e));
         return OPP_ERR_CUDA;
     }
-    cudaEventElapsedTime(&s.last_ms, s.ev_start, s.ev_done);
+    s.ms_pending = !retired; // the kernel may still be retiring: opp_last_batch_ms reads the events when asked
+    if (retired) cudaEventElapsedTime(&s.last_ms, s.ev_start, s.ev_done);
     if (h->trace) {
         float t[8] = {0};
         cudaEventElapsedTime(&t[6], h->trace_base, s.ev_start);
@@ -791,7 +858,13 @@ float opp_last_batch_ms(opp_handle_t h, int ticket)
 {
     if (!h) return -1.f;
     Slot *s = slot_of(h, ticket);
-    return s ? s->last_ms : -1.f;
+    if (!s) return -1.f;
+    if (s->ms_pending && !s->busy) {
+        DeviceGuard guard_(h->device);
+        if (cudaEventSynchronize(s->ev_done) == cudaSuccess) cudaEventElapsedTime(&s->last_ms, s->ev_start, s->ev_done);
+        s->ms_pending = false;
+    }
+    return s->last_ms;
 }
 
 int64_t opp_launch_count(opp_handle_t h) { return h ? h->launches : 0; }
@@ -806,6 +879,7 @@ int opp_debug_fetch(opp_handle_t h, int ticket, int what, int frame, int index, 
     Slot &s = *sp;
     DeviceGuard guard_(h->device);
     const int capP = h->cfg.max_peaks_per_part, capH = h->cfg.max_humans;
+    cudaStreamSynchronize(s.stream); // opp_wait may have returned on the completion word while the kernel was still retiring
     auto d2h = [&](void *d, const void *src, size_t bytes) { return cudaMemcpy(d, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess; };
     switch (what) {
     case OPP_DBG_PEAKS: {

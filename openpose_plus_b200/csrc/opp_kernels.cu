@@ -1457,6 +1457,15 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
         if (p.flags_out) p.flags_out[frame] = all;
         p.stats[frame * 4 + 0] = s_state[0];
         p.stats[frame * 4 + 1] = s_state[3];
+        if (p.host_done) {
+            // The barrier above orders every thread's records before this point; the fence is cumulative, so they
+            // are visible system-wide before the completion word is (barrier, one thread fences, one thread signals).
+            __threadfence_system();
+            if (atomicAdd(p.batch_done, 1) == p.done_frames - 1) {
+                if (p.done_frames > 1) __threadfence_system(); // the other frames' records, observed through the counter
+                *reinterpret_cast<volatile int *>(p.host_done) = p.done_tag;
+            }
+        }
     }
 }
 

@@ -73,6 +73,12 @@ struct K3Params {
     // shared-memory carve-up (byte offsets)
     int off_paf, off_pk, off_cand, off_used, off_misc, off_href, off_score, off_conn, off_keep, off_owner;
     float thr_vec, thr_human;
+    // completion word for the latency path: every frame's assembly bumps batch_done; the one that completes the batch
+    // writes done_tag to host_done (mapped pinned memory) after a system-scope fence, so the host can spin on it
+    // instead of waiting for the kernel to retire and an event to be signalled.  host_done == nullptr: unused.
+    int *batch_done;
+    int *host_done;
+    int done_tag, done_frames;
     int true_index;            // assembly indexes humans by position (pafprocess) instead of by stored id (src/paf.cpp:198,204)
     unsigned long long *times; // optional [n][19][12] %globaltimer stamps of the phases (debug), may be null
 };
