@@ -90,6 +90,7 @@ struct opp_handle_s {
     bool fuse_resize = true;
     bool k2_skip = true;
     bool zero_copy_out = true;
+    bool paf_early = true; // latency path: the limb kernel fetches its PAF tiles from pinned memory itself (OPP_NO_PAF_EARLY=1 disables)
     bool done_flag = true; // completion word in pinned memory on the latency path (OPP_NO_DONE_FLAG=1 disables)
     int tag_seq = 0;
     bool pdl = true; // programmatic dependent launch on the latency path (OPP_NO_PDL=1 disables)
@@ -504,6 +505,7 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
         h->zero_copy_out = getenv("OPP_NO_ZEROCOPY_OUT") == nullptr;
         h->pdl = getenv("OPP_NO_PDL") == nullptr;
         h->done_flag = getenv("OPP_NO_DONE_FLAG") == nullptr;
+        h->paf_early = getenv("OPP_NO_PAF_EARLY") == nullptr;
         if (const char *e = getenv("OPP_ZC_IN_MAX")) h->zero_copy_in_max = atoi(e);
         if (const char *e = getenv("OPP_INGEST_MAX")) h->ingest_max = atoi(e);
         CU(cudaStreamCreateWithFlags(&h->timer_stream, cudaStreamNonBlocking));
@@ -543,6 +545,8 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     cudaStream_t st = s.stream;
     CU(cudaEventRecord(s.ev_start, st));
     const bool ingest = b.in_mem == OPP_MEM_HOST && b.in_layout == OPP_LAYOUT_CHW && n <= h->ingest_max && mapped_host(b.conf) && mapped_host(b.paf);
+    // (the limb kernel can only be scheduled early when no up-sampled maps are written on a side stream in between)
+    const bool paf_early = ingest && h->pdl && h->paf_early && h->fast_k2 && h->k3_plan.paf_in_smem && !h->trace && !b.conf_up && !b.paf_up;
     if (!ingest) CU(cudaMemsetAsync(s.d_counters, 0, h->counters_ints * sizeof(int), st));
 
     // ---- inputs
@@ -564,6 +568,13 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
         CU(launch_hwc_to_chw(src, s.d_paf, n, OPP_N_PAF, g.h, g.w, st));
         h->launches += 2;
         conf = s.d_conf, paf = s.d_paf;
+    } else if (ingest && paf_early) {
+        // only the heat maps (and the counter reset) go through the ingest kernel; the limb kernel, scheduled early by
+        // programmatic dependent launch, pulls each limb's PAF tile from the pinned buffer while the peak kernel runs
+        CU(launch_ingest((const float *)mapped_host(b.conf), s.d_conf, (size_t)n * OPP_N_HEAT * hw, nullptr, nullptr, 0, s.d_counters,
+                         (int)h->counters_ints, st));
+        h->launches += 1;
+        conf = s.d_conf, paf = (const float *)mapped_host(b.paf);
     } else if (ingest) {
         CU(launch_ingest((const float *)mapped_host(b.conf), s.d_conf, (size_t)n * OPP_N_HEAT * hw, (const float *)mapped_host(b.paf), s.d_paf,
                          (size_t)n * OPP_N_PAF * hw, s.d_counters, (int)h->counters_ints, st));
@@ -694,6 +705,7 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
         k3.done_tag = s.done_tag, k3.done_frames = n;
         if (!k3.host_done) s.done_tag = 0;
     }
+    k3.paf_early = paf_early;
     k3.true_index = c.variant == OPP_VARIANT_PYTHON;
     k3.thr_vec = 0.05f, k3.thr_human = 0.4f; // THRESH_VECTOR_SCORE, THRESH_HUMAN_SCORE, src/paf.cpp:61,64
     CU(launch_k3(k3, n, h->k3_smem, st, pdl && h->fast_k2));

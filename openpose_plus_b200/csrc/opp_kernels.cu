@@ -536,8 +536,9 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
     float *Rrow = smem + ((nr * w + 3) & ~3); // [nr][RW] row-pass result
     float *Pf = Rrow + ((nr * RW + 3) & ~3);  // [2][ib-ia][w] PAF feature rows of the tile (STORE only)
     const float *src = p.conf + ((size_t)frame * OPP_N_HEAT + part) * h * w + ilo * w;
+    pdl_trigger(); // the limb kernel may be scheduled behind this grid at once (it can fetch PAF tiles from pinned memory
+                   // meanwhile); it waits for our completion itself before touching the peaks
     pdl_wait();    // the maps (and the counters) may come from an ingest kernel still in flight
-    pdl_trigger(); // the limb kernel may be scheduled behind this grid; it waits for our completion itself
     stage_async(L, src, nr * w);
     if (STORE) {
         // staged up front: a load issued next to the store stream would queue behind it for microseconds
@@ -1479,12 +1480,31 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
     const int h = p.g.h, w = p.g.w, capP = p.capP, capC = p.capC;
     const int pa = c_pair_a[pair_id], pb = c_pair_b[pair_id], cx = c_net_x[pair_id]; // the y channel is the next plane
     const int *pofs = p.part_ofs + frame * (OPP_N_PARTS + 1);
+    float *s_paf = reinterpret_cast<float *>(smem_raw + p.off_paf);      // [2][h*w]
+    __shared__ unsigned long long s_mbar;
+    bool paf_bulk = false;
+    // the x and y channels of a limb are adjacent planes: one contiguous tile of 2*h*w floats
+    const float *gpx = p.paf + ((size_t)frame * OPP_N_PAF + cx) * h * w;
+    auto fetch_paf_tile = [&]() {
+        paf_bulk = ((reinterpret_cast<uintptr_t>(gpx) | (uintptr_t)(2 * h * w * sizeof(float))) & 15) == 0;
+        if (paf_bulk) {
+            if (tid == 0) {
+                bulk_init(&s_mbar);
+                bulk_load(s_paf, gpx, (unsigned)(2 * h * w * sizeof(float)), &s_mbar);
+            }
+        } else {
+            stage_async(s_paf, gpx, 2 * h * w);
+        }
+    };
+    // Latency path: the PAFs are still in the caller's pinned host memory and nothing the preceding kernels produce is
+    // needed to fetch them, so the tile starts its trip over PCIe before this CTA waits for the peak kernel.
+    const bool paf_early = p.paf_early && p.paf_in_smem;
+    if (paf_early) fetch_paf_tile();
     pdl_wait(); // peaks come from the peak kernel, which may still be running when this CTA is scheduled
     const int ofs_a = __ldcg(pofs + pa), na = __ldcg(pofs + pa + 1) - ofs_a;
     const int ofs_b = __ldcg(pofs + pb), nb = __ldcg(pofs + pb + 1) - ofs_b;
     const opp_peak_t *peaks = p.peaks + (size_t)frame * OPP_N_PARTS * capP;
 
-    float *s_paf = reinterpret_cast<float *>(smem_raw + p.off_paf);      // [2][h*w]
     int2 *s_pa = reinterpret_cast<int2 *>(smem_raw + p.off_pk);          // [capP]
     int2 *s_pb = s_pa + capP;                                            // [capP]
     unsigned char *s_used = smem_raw + p.off_used;                       // [2*capP]
@@ -1501,23 +1521,11 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
     stamp(p, frame, pair_id, 0);
     int n_cand = 0;
     const long n_pairs = (long)na * nb;
-    __shared__ unsigned long long s_mbar;
-    bool paf_bulk = false;
     if (n_pairs > 0) {
-        const float *gpx = p.paf + ((size_t)frame * OPP_N_PAF + cx) * h * w;
         const float *gpy = gpx + h * w;
         const float *px_plane = gpx, *py_plane = gpy;
         if (p.paf_in_smem) {
-            // the x and y channels of a limb are adjacent planes: one contiguous tile of 2*h*w floats
-            paf_bulk = ((reinterpret_cast<uintptr_t>(gpx) | (uintptr_t)(2 * h * w * sizeof(float))) & 15) == 0;
-            if (paf_bulk) {
-                if (tid == 0) {
-                    bulk_init(&s_mbar);
-                    bulk_load(s_paf, gpx, (unsigned)(2 * h * w * sizeof(float)), &s_mbar);
-                }
-            } else {
-                stage_async(s_paf, gpx, 2 * h * w);
-            }
+            if (!paf_early) fetch_paf_tile();
             px_plane = s_paf, py_plane = s_paf + h * w;
         }
         for (int t = tid; t < na; t += blockDim.x) s_pa[t] = make_int2(__ldcg(&peaks[ofs_a + t].x), __ldcg(&peaks[ofs_a + t].y));
@@ -1651,8 +1659,13 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
             p.n_conns[frame * OPP_N_PAIRS + pair_id] = nc;
             atomicAdd(p.stats + frame * 4 + 2, n_cand);
         }
-    } else if (tid == 0) {
-        p.n_conns[frame * OPP_N_PAIRS + pair_id] = 0;
+    } else {
+        if (tid == 0) p.n_conns[frame * OPP_N_PAIRS + pair_id] = 0;
+        if (paf_early) { // the tile was requested anyway: it must have landed before the shared memory is reused
+            stage_wait();
+            __syncthreads();
+            if (paf_bulk) bulk_wait(&s_mbar, 0);
+        }
     }
 
     stamp(p, frame, pair_id, 4);

@@ -79,6 +79,7 @@ struct K3Params {
     int *batch_done;
     int *host_done;
     int done_tag, done_frames;
+    int paf_early;             // paf is mapped pinned host memory: each CTA requests its tile before griddepcontrol.wait
     int true_index;            // assembly indexes humans by position (pafprocess) instead of by stored id (src/paf.cpp:198,204)
     unsigned long long *times; // optional [n][19][12] %globaltimer stamps of the phases (debug), may be null
 };
