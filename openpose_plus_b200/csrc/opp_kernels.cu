@@ -1066,7 +1066,18 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
     const int n_peaks = __ldcg(pofs + OPP_N_PARTS);
     const opp_peak_t *peaks = p.peaks + (size_t)frame * OPP_N_PARTS * capP;
     const bool all_conns = p.conns_in_smem != 0, pk_smem = p.score_in_smem != 0;
-    if (threadIdx.x < OPP_N_PAIRS) s_nc[threadIdx.x] = __ldcg(p.n_conns + frame * OPP_N_PAIRS + threadIdx.x);
+    if (threadIdx.x < 32) { // connection counts of the 19 limbs and their exclusive prefix sums, one warp scan
+        const int ln = threadIdx.x;
+        const int nc = ln < OPP_N_PAIRS ? __ldcg(p.n_conns + frame * OPP_N_PAIRS + ln) : 0;
+        int incl = nc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (ln >= o) incl += v;
+        }
+        if (ln < OPP_N_PAIRS) s_nc[ln] = nc, s_coff[ln + 1] = incl;
+        if (ln == 0) s_coff[0] = 0;
+    }
     if (threadIdx.x >= 32 && threadIdx.x < 40) s_state[threadIdx.x - 32] = 0;
     // Forest form of the 17 tree limbs (see below): s_c1[limb][local index of a first-part peak] = flattened index of
     // the limb's connection that starts at that peak (0xffff: none); s_in = bitmap over peak ids, set when the peak
@@ -1089,27 +1100,22 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
         for (int t = threadIdx.x; t < n_peaks; t += blockDim.x)
             s_pk[t] = make_int2(__ldcg(&peaks[t].x) | (__ldcg(&peaks[t].y) << 16), __float_as_int(__ldcg(&peaks[t].score)));
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int o = 0;
-        for (int l = 0; l < OPP_N_PAIRS; ++l) s_coff[l] = o, o += s_nc[l];
-        s_coff[OPP_N_PAIRS] = o;
-    }
-    __syncthreads();
-    if (all_conns) { // every connection of the frame in ONE round trip
-        const int total = s_coff[OPP_N_PAIRS];
-        for (int t = threadIdx.x; t < total; t += blockDim.x) {
-            int l = 0;
-            while (l + 1 < OPP_N_PAIRS && s_coff[l + 1] <= t) ++l;
-            const opp_conn_t *g = p.conns + ((size_t)frame * OPP_N_PAIRS + l) * capP + (t - s_coff[l]);
-            opp_conn_t c;
-            c.cid1 = __ldcg(&g->cid1), c.cid2 = __ldcg(&g->cid2), c.score = __ldcg(&g->score);
-            s_conn[t] = c;
-            if (use_owner) {
-                s_lmb[t] = (unsigned char)l;
-                if (l < 17) {
-                    const int la = c.cid1 - s_pofs[s_pa[l]];
-                    if (la >= 0 && la < capP) s_c1[l * capP + la] = (unsigned short)t;
-                    if (c.cid2 >= 0 && c.cid2 < OPP_N_PARTS * capP) atomicOr(&s_in[c.cid2 >> 5], 1u << (c.cid2 & 31));
+    if (all_conns) { // every connection of the frame in ONE round trip: the warps take the limbs in turn, a lane per connection
+        for (int l = threadIdx.x >> 5; l < OPP_N_PAIRS; l += blockDim.x >> 5) {
+            const int nc = s_nc[l], base = s_coff[l], pa_ofs = s_pofs[s_pa[l]];
+            const opp_conn_t *g = p.conns + ((size_t)frame * OPP_N_PAIRS + l) * capP;
+            for (int k = threadIdx.x & 31; k < nc; k += 32) {
+                const int t = base + k;
+                opp_conn_t c;
+                c.cid1 = __ldcg(&g[k].cid1), c.cid2 = __ldcg(&g[k].cid2), c.score = __ldcg(&g[k].score);
+                s_conn[t] = c;
+                if (use_owner) {
+                    s_lmb[t] = (unsigned char)l;
+                    if (l < 17) {
+                        const int la = c.cid1 - pa_ofs;
+                        if (la >= 0 && la < capP) s_c1[l * capP + la] = (unsigned short)t;
+                        if (c.cid2 >= 0 && c.cid2 < OPP_N_PARTS * capP) atomicOr(&s_in[c.cid2 >> 5], 1u << (c.cid2 & 31));
+                    }
                 }
             }
         }
@@ -1240,6 +1246,14 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
         int created = 0;          // humans created so far (uniform over the CTA)
         int *s_create = s_keep;   // [capH] creating connection of each human (s_keep is not in use yet)
         const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        int tflags = 0;
+        auto pscore = [&](int id) -> float {
+            if (id < 0 || id >= n_peaks) {
+                tflags |= OPP_FLAG_UB_PEAK_INDEX;
+                return 0.f;
+            }
+            return pk_smem ? __int_as_float(s_pk[id].y) : __ldcg(&peaks[id].score);
+        };
         for (int base = 0; base < T; base += blockDim.x) {
             const int t = base + threadIdx.x;
             bool creator = false;
@@ -1280,10 +1294,16 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
                     hq[HR_PART + s_pa[l]] = c.cid1, hq[HR_PART + s_pb[l]] = c.cid2;
                 }
             }
+            // What this connection adds to its human's score, in place of its own score (nothing else reads a tree
+            // limb's score from shared memory): the creating one opens the sum with (s(cid1) + s(cid2)) + score
+            // (src/paf.cpp:243-244), every other one is added as (s(cid2) + score) (:205-209).
+            if (t < T) {
+                const float s2 = pscore(c.cid2);
+                s_conn[t].score = creator ? __fadd_rn(__fadd_rn(pscore(c.cid1), s2), c.score) : __fadd_rn(s2, c.score);
+            }
             created += total;
             __syncthreads();
         }
-        int tflags = 0;
         if (created > capH) tflags |= OPP_FLAG_HUMAN_OVERFLOW, created = capH;
         // Parts: a human's skeleton below its creating connection is at most three limbs deep (neck - shoulder - elbow -
         // wrist, neck - hip - knee - ankle, neck - nose - eye - ear), so three rounds over (human, limb) settle every part.
@@ -1302,32 +1322,25 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
             }
             __syncthreads();
         }
-        auto pscore = [&](int id) -> float {
-            if (id < 0 || id >= n_peaks) {
-                tflags |= OPP_FLAG_UB_PEAK_INDEX;
-                return 0.f;
-            }
-            return pk_smem ? __int_as_float(s_pk[id].y) : __ldcg(&peaks[id].score);
-        };
         // Score and part count: the creating connection first (src/paf.cpp:243-244), then the human's connection of every
         // later limb in limb order, each as (s(cid2) + conn.score) (:205-209).  The lookups of different limbs are
         // independent now; only the additions are a chain.
         for (int q = threadIdx.x; q < created; q += blockDim.x) {
             int *hq = hr + q * HR_WORDS;
             const int t0 = s_create[q], l0 = s_lmb[t0];
-            const opp_conn_t c0 = s_conn[t0];
-            float sc = __fadd_rn(__fadd_rn(pscore(c0.cid1), pscore(c0.cid2)), c0.score);
+            float sc = s_conn[t0].score;
             int np = 2;
+            // no branches: the 17 look-ups are independent of each other and can all be in flight; only the additions chain
 #pragma unroll
             for (int l = 0; l < 17; ++l) {
                 const int held = hq[HR_PART + c_pair_a[l]];
                 const int la = held - s_pofs[c_pair_a[l]];
-                if (l == l0 || held < 0 || la < 0 || la >= capP) continue;
-                const int t = s_c1[l * capP + la];
-                if (t == 0xffff) continue;
-                const opp_conn_t c = s_conn[t];
-                sc = __fadd_rn(sc, __fadd_rn(pscore(c.cid2), c.score));
-                ++np;
+                const bool in = l != l0 && held >= 0 && la >= 0 && la < capP;
+                const int t = s_c1[l * capP + (in ? la : 0)];
+                const bool on = in && t != 0xffff;
+                const float v = s_conn[on ? t : t0].score;
+                sc = on ? __fadd_rn(sc, v) : sc;
+                np += on;
             }
             hq[HR_NPARTS] = np, hq[HR_SCORE] = __float_as_int(sc);
         }
