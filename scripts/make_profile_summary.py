@@ -27,7 +27,7 @@ shutil.copy(os.path.join(G, "bench_ref.json"), os.path.join(P, tag + "_bench_ref
 
 out = ["# profiles/ — round 1 (B200, sm_100a)\n"]
 out.append("All captures: `gpurun` on one B200, `ncu --clock-control none`, command `python bench.py --steps 3 --warmup 3 --no-cpu-baseline "
-           "--no-other-configs`, taken only after the same command exited 0 without ncu. Timings under ncu are cold-cache and serialised: compare "
+           "--no-other-configs` (the whole pass is `scripts/profile_run.sh`), taken only after the same command exited 0 without ncu. Timings under ncu are cold-cache and serialised: compare "
            "shares, not absolutes; the bench numbers are CUDA-event timings from a plain run. Regenerate with `scripts/make_profile_summary.py`.\n")
 b = json.load(open(os.path.join(P, tag + "_bench.json")))
 r = json.load(open(os.path.join(P, tag + "_bench_reference.json")))
@@ -36,7 +36,8 @@ out.append("| quantity | value |\n|---|---|")
 out.append("| value (materialised, device-resident maps) | %.0f frames/s (%.3f ms / 64-frame step) |" % (b["value"], b["ms_per_step"]))
 out.append("| fused (skeleton-only, C++ contract) | %.0f frames/s |" % b["fused"]["value"])
 out.append("| e2e (pinned host maps in, skeletons out) | %.0f frames/s (H2D %.1f MB/step: PCIe-bound) |" % (b["e2e"]["value"], b["e2e"]["h2d_bytes_per_step"] / 1e6))
-out.append("| p50 latency, 1 frame, host buffers | %.4f ms |" % b["latency_ms_p50"])
+out.append("| p50 latency, 1 frame, pinned host buffers, through the Python engine | %.4f ms on the idle GPU, %.4f ms right after the sustained runs |"
+           % (b["latency_ms_p50"], b.get("latency_ms_p50_after_load", float("nan"))))
 out.append("| roofline, dominant kernel of the materialised step (peaks + resize fused) | %.0f GB/s = %.3f of measured %.1f GB/s; ncu traffic %.3f GB vs %.3f GB algorithmic |"
            % (b["roofline"]["achieved"], b["roofline"]["frac"], b["roofline"]["peak"], (b["roofline"].get("traffic") or 0) / 1e9, b["roofline"]["algorithmic_bytes_per_launch"] / 1e9))
 out.append("| stand-alone resize kernel | %.0f GB/s = %.3f |" % (b["roofline_k1"]["achieved"], b["roofline_k1"]["frac"]))
@@ -76,6 +77,6 @@ out.append("SASS evidence (`cuobjdump -sass openpose_plus_b200/libopp_b200.so`):
            "(TMA bulk load of the PAF tile in `k3_limbs`, mbarrier completion), `UBLKCP.G.S` (TMA bulk-store resize variant), `LDGSTS` (cp.async tile "
            "staging in `k2_peaks_fast`), `STG.E.EF.128` (streaming 16-byte stores of the up-sampled maps). No tensor-core instructions: no stage is a contraction.\n")
 out.append("compute-sanitizer is closed on this pool (the tool answers so); memory safety is covered by capacity checks in the kernels, the overflow "
-           "flags and the stage-by-stage comparison with the CPU oracle on 27 GPU tests.\n")
+           "flags and the stage-by-stage comparison with the CPU oracle in the GPU tests (`pytest -m gpu`).\n")
 open(os.path.join(P, "README.md"), "w").write("\n".join(out))
 print("\n".join(out)[:1500])

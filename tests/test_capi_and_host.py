@@ -213,3 +213,66 @@ int main() {
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         assert subprocess.run([exe]).returncode == 0
+
+
+class _FakeEngine:
+    """Stands in for Engine in host-logic tests: records what was submitted and writes frame indices as results."""
+
+    def __init__(self, max_batch=8, n_slots=3, max_humans=4, fail_at=None):
+        import types
+        self.max_batch, self.max_humans, self.cfg = max_batch, max_humans, types.SimpleNamespace(n_slots=n_slots)
+        self.calls, self.inflight, self.peak_inflight, self.fail_at = [], 0, 0, fail_at
+
+    def submit(self, conf, paf, out=None, **kw):
+        assert conf.shape[0] <= self.max_batch and self.inflight < self.cfg.n_slots
+        if self.fail_at is not None and len(self.calls) == self.fail_at:
+            raise capi.OppError(2, "injected")
+        self.inflight += 1
+        self.peak_inflight = max(self.peak_inflight, self.inflight)
+        self.calls.append((conf, out))
+        return len(self.calls) - 1
+
+    def wait(self, t):
+        conf, (humans, counts, flags) = self.calls[t]
+        counts[:] = conf[:, 0, 0, 0].astype(np.int32)          # "number of humans" = the frame's tag
+        humans["score"][:, 0] = conf[:, 0, 0, 0]
+        flags[:] = 0
+        self.inflight -= 1
+        return humans, counts, flags
+
+
+def test_stream_drivers_shard_order_and_pipeline_depth():
+    """process_stream / process_stream_multi: contiguous shards, frame order kept, all slots used and never exceeded,
+    ragged tails, more GPUs than frames, and an engine failure surfacing on the caller's thread."""
+    from openpose_plus_b200.sharding import process_stream, process_stream_multi
+    n = 53
+    conf = np.zeros((n, 19, 2, 2), np.float32)
+    conf[:, 0, 0, 0] = np.arange(n)
+    paf = np.zeros((n, 38, 2, 2), np.float32)
+    for world in (1, 2, 3, 8):
+        engines = [_FakeEngine() for _ in range(world)]
+        humans, counts, flags = process_stream_multi(engines, conf, paf)
+        assert counts.tolist() == list(range(n)) and humans["score"][:, 0].tolist() == list(range(n))
+        assert sum(sum(c[0].shape[0] for c in e.calls) for e in engines) == n
+        assert all(e.inflight == 0 and e.peak_inflight <= 3 for e in engines)
+        if n // world >= 3 * 8:                                 # enough batches per GPU to fill every slot
+            assert all(e.peak_inflight == 3 for e in engines)
+    e = _FakeEngine()
+    h, c, f = process_stream(e, conf, paf, rank=0, world=1, batch=5)
+    assert c.tolist() == list(range(n)) and [x[0].shape[0] for x in e.calls] == [5] * 10 + [3]
+    few = process_stream_multi([_FakeEngine() for _ in range(8)], conf[:3], paf[:3])      # more GPUs than frames
+    assert few[1].tolist() == [0, 1, 2]
+    with pytest.raises(capi.OppError):
+        process_stream_multi([_FakeEngine(), _FakeEngine(fail_at=1)], conf, paf)
+
+
+def test_engine_takes_buffer_addresses_without_ndarray_ctypes():
+    from openpose_plus_b200.engine import _ptr
+    a = np.zeros((4, 5), np.float32)
+    ro = a.view()
+    ro.flags.writeable = False
+    rec = np.zeros((2, 3), capi.HUMAN_DT)
+    assert _ptr(a) == a.ctypes.data and _ptr(a[1:]) == a[1:].ctypes.data and _ptr(ro) == a.ctypes.data
+    assert _ptr(rec[1:]) == rec[1:].ctypes.data and _ptr(None) is None
+    with pytest.raises(TypeError):
+        _ptr([1, 2, 3])
