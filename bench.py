@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--slots", type=int, default=3)
+    ap.add_argument("--latency-iters", type=int, default=320, help="one-frame calls per p50 latency measurement (the first 20 are warm-up)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -278,11 +279,11 @@ def main():
     def latency_p50():
         lat = []
         one = (h_ring[0][0][:1], h_ring[0][1][:1])
-        for i in range(320):
+        for i in range(max(args.latency_iters, 1)):
             t0 = time.perf_counter()
             eng.process(one[0], one[1], out=(outs[0][0][:1], outs[0][1][:1], outs[0][2][:1]))
             lat.append((time.perf_counter() - t0) * 1e3)
-        v = statistics.median(lat[20:])
+        v = statistics.median(lat[20:] if len(lat) > 40 else lat)
         if world > 1:
             t = torch.tensor([v], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -27,7 +27,7 @@ shutil.copy(os.path.join(G, "bench_ref.json"), os.path.join(P, tag + "_bench_ref
 
 out = ["# profiles/ — round 1 (B200, sm_100a)\n"]
 out.append("All captures: `gpurun` on one B200, `ncu --clock-control none`, command `python bench.py --steps 3 --warmup 3 --no-cpu-baseline "
-           "--no-other-configs` (the whole pass is `scripts/profile_run.sh`), taken only after the same command exited 0 without ncu. Timings under ncu are cold-cache and serialised: compare "
+           "--no-other-configs --latency-iters 8` (the whole pass is `scripts/profile_run.sh`), taken only after the same command exited 0 without ncu. Timings under ncu are cold-cache and serialised: compare "
            "shares, not absolutes; the bench numbers are CUDA-event timings from a plain run. Regenerate with `scripts/make_profile_summary.py`.\n")
 b = json.load(open(os.path.join(P, tag + "_bench.json")))
 r = json.load(open(os.path.join(P, tag + "_bench_reference.json")))
