@@ -290,8 +290,23 @@ def main():
             v = float(t[0])
         return v
 
+    # the same call from C (opp_bench_latency loops over opp_process inside the library): what a C++ paf_processor
+    # caller sees, without the interpreter's share of every call
+    def latency_p50_capi():
+        import ctypes as C
+        b = capi.Batch()
+        one = (h_ring[0][0][:1], h_ring[0][1][:1])
+        b.conf, b.paf, b.n_frames = one[0].ctypes.data, one[1].ctypes.data, 1
+        b.in_mem, b.in_layout, b.out_mem = capi.MEM_HOST, capi.LAYOUT_CHW, capi.MEM_HOST
+        b.humans, b.n_humans, b.frame_flags = outs[0][0].ctypes.data, outs[0][1].ctypes.data, outs[0][2].ctypes.data
+        n_it = max(args.latency_iters, 1)
+        us = np.zeros(n_it, np.float32)
+        eng._check(eng.L.opp_bench_latency(eng.h, C.byref(b), n_it, us.ctypes.data))
+        return float(np.median(us[20:] if n_it > 40 else us)) * 1e-3
+
     barrier()
     lat_p50 = latency_p50()
+    lat_p50_capi = latency_p50_capi()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -419,6 +434,7 @@ def main():
             "fused": {"value": N * f_frames / (f_dev_ms * 1e-3), "unit": "frames/s", "note": "skeletons only (C++ paf_processor contract): up-sampled maps never written to HBM"},
             "latency_ms_p50": lat_p50,
             "latency_ms_p50_after_load": lat_p50_loaded,
+            "latency_ms_p50_capi": lat_p50_capi,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k2_peaks_fast<8,8,STORE> (resize of the 19+38 maps fused into smooth + NMS + peak list)",
                          "achieved": k2s_gbs, "peak": peak, "unit": "GB/s", "frac": k2s_gbs / peak, "traffic": ncu_traffic("r1_final_k2store_ncu_raw.csv"),

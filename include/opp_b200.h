@@ -186,6 +186,11 @@ float opp_timer_stop(opp_handle_t h);
  * row_stride_bytes = 0 means width * channels.  Host code; needs no GPU and no handle. */
 int opp_draw_human(uint8_t *image, int height, int width, int channels, ptrdiff_t row_stride_bytes, const opp_human_t *human, int thickness);
 
+/* Calls opp_process(h, batch) `iters` times from C and writes each call's wall-clock duration in microseconds to
+ * out_us[iters] (std::chrono::steady_clock around the call): the latency a C or C++ caller of this ABI sees, without
+ * the interpreter overhead a Python loop adds to every call.  Returns the status of the first failing call. */
+int opp_bench_latency(opp_handle_t h, const opp_batch_t *batch, int iters, float *out_us);
+
 const char *opp_last_error(opp_handle_t h);
 const char *opp_version(void);
 

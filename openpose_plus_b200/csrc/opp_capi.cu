@@ -1,6 +1,7 @@
 // Host runtime behind the C-ABI of include/opp_b200.h: per-GPU handle, pipeline slots (own stream,
 // device arena, pinned result buffers), and the stage sequencing that replaces
 // paf_processor_impl::operator() (/root/reference src/paf.cpp:38-57).
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
@@ -864,6 +865,19 @@ int opp_process(opp_handle_t h, const opp_batch_t *b)
     int rc = opp_submit(h, b, &t);
     if (rc != OPP_OK) return rc;
     return opp_wait(h, t);
+}
+
+int opp_bench_latency(opp_handle_t h, const opp_batch_t *batch, int iters, float *out_us)
+{
+    if (!h || !batch || !out_us || iters < 1) return OPP_ERR_INVALID;
+    for (int i = 0; i < iters; ++i) {
+        const auto t0 = std::chrono::steady_clock::now();
+        const int rc = opp_process(h, batch);
+        const auto t1 = std::chrono::steady_clock::now();
+        if (rc != OPP_OK) return rc;
+        out_us[i] = std::chrono::duration<float, std::micro>(t1 - t0).count();
+    }
+    return OPP_OK;
 }
 
 float opp_last_batch_ms(opp_handle_t h, int ticket)
