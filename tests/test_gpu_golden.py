@@ -252,3 +252,47 @@ def test_single_process_multi_gpu_stream(mods):
     assert np.array_equal(counts, c1) and np.array_equal(flags, f1)
     for f in range(0, 1000, 37):
         assert H.humans_equal(humans[f, :counts[f]], h1[f, :c1[f]]) is None
+
+
+def test_latency_path_pipelined_single_frames(mods, monkeypatch):
+    """One-frame batches in pinned memory take the latency path (ingest kernel for the heat maps, programmatic
+    dependent launch, PAF tiles fetched from pinned memory by the limb kernel, completion word).  Three of them in
+    flight on three slots, pinned and pageable result buffers, and every switch of that path turned off in turn must all
+    give the batch path's answer."""
+    Engine, capi, H = mods
+    conf, paf = synth.render_batch(12, n_people=6, seed0=1200)
+    ref_eng = Engine(46, 54, max_batch=12)
+    want_h, want_c, want_f = ref_eng.process(conf, paf)
+    hc, hp = capi.pinned_empty(conf.shape, np.float32), capi.pinned_empty(paf.shape, np.float32)
+    hc[...] = conf
+    hp[...] = paf
+
+    def run(pinned_out):
+        eng = Engine(46, 54, max_batch=4, n_slots=3)
+        if pinned_out:
+            outs = [(capi.pinned_empty((1, eng.max_humans), capi.HUMAN_DT), capi.pinned_empty((1,), np.int32), capi.pinned_empty((1,), np.int32)) for _ in range(12)]
+        else:
+            outs = [(np.zeros((1, eng.max_humans), capi.HUMAN_DT), np.zeros(1, np.int32), np.zeros(1, np.int32)) for _ in range(12)]
+        inflight = []
+        for f in range(12):
+            if len(inflight) == 3:
+                eng.wait(inflight.pop(0))
+            inflight.append(eng.submit(hc[f:f + 1], hp[f:f + 1], out=outs[f]))
+        for t in inflight:
+            eng.wait(t)
+        for f in range(12):
+            h, c, fl = outs[f]
+            assert c[0] == want_c[f] and fl[0] == want_f[f], f
+            assert H.humans_equal(h[0, :c[0]], want_h[f, :want_c[f]]) is None, f
+        t = eng.submit(hc[3:5], hp[3:5])                          # two frames: still the latency path
+        two = eng.wait(t)
+        assert np.array_equal(two[1], want_c[3:5]) and H.humans_equal(two[0][1, :two[1][1]], want_h[4, :want_c[4]]) is None
+        assert 0 < eng.last_batch_ms(t) < 5                       # read from the events lazily, after the completion word
+        eng.close()
+
+    run(True)
+    run(False)
+    for switch in ("OPP_NO_PDL", "OPP_NO_PAF_EARLY", "OPP_NO_DONE_FLAG"):
+        monkeypatch.setenv(switch, "1")
+        run(True)
+        monkeypatch.delenv(switch)
