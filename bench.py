@@ -388,6 +388,11 @@ def main():
             "736x864_b32_12people": {"materialised": other_config(92, 108, 12, 32, True), "skeleton_only": other_config(92, 108, 12, 32, False), "unit": "frames/s"},
             "368x432_b64_crowded_32people": {"materialised": other_config(46, 54, 32, 64, True, max_humans=256),
                                              "skeleton_only": other_config(46, 54, 32, 64, False, max_humans=256), "unit": "frames/s"},
+            # the semantics of the reference's Python graph (k = 25 CDF-derived kernel, zero border,
+            # pafprocess-style grouping); outside the fast peak kernel's range, replication-aware generic kernel
+            "368x432_b64_python_variant_k25": {"materialised": other_config(46, 54, PEOPLE, 64, True, gauss_kernel_size=25, variant=capi.VARIANT_PYTHON),
+                                               "skeleton_only": other_config(46, 54, PEOPLE, 64, False, gauss_kernel_size=25, variant=capi.VARIANT_PYTHON),
+                                               "unit": "frames/s"},
         }
 
     cpu_baseline = None

@@ -94,6 +94,7 @@ struct opp_handle_s {
     bool paf_early = true; // latency path: the limb kernel fetches its PAF tiles from pinned memory itself (OPP_NO_PAF_EARLY=1 disables)
     bool done_flag = true; // completion word in pinned memory on the latency path (OPP_NO_DONE_FLAG=1 disables)
     int tag_seq = 0;
+    bool generic_rep = true; // integer scales outside the fast kernel's range: replication-aware generic kernel (OPP_NO_GENERIC_REP=1: via the materialised map)
     bool pdl = true; // programmatic dependent launch on the latency path (OPP_NO_PDL=1 disables)
     int zero_copy_in_max = 0; // kernels reading pinned host maps in place: measured slower than staging them (kept for experiments)
     int ingest_max = 4;       // up to this many frames, pinned host maps are pulled in by one kernel instead of memset + 2 DMA copies
@@ -505,6 +506,7 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
         h->k2_skip = getenv("OPP_K2_NOSKIP") == nullptr;
         h->zero_copy_out = getenv("OPP_NO_ZEROCOPY_OUT") == nullptr;
         h->pdl = getenv("OPP_NO_PDL") == nullptr;
+        h->generic_rep = getenv("OPP_NO_GENERIC_REP") == nullptr;
         h->done_flag = getenv("OPP_NO_DONE_FLAG") == nullptr;
         h->paf_early = getenv("OPP_NO_PAF_EARLY") == nullptr;
         if (const char *e = getenv("OPP_ZC_IN_MAX")) h->zero_copy_in_max = atoi(e);
@@ -595,7 +597,10 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
 
     // ---- optional materialised up-sampled maps, beside the rest (they are outputs only)
     const bool want_up = b.conf_up || b.paf_up;
-    const bool generic_needs_conf_up = !h->fast_k2;
+    // the generic peak kernel reads a materialised heat map only at non-integer scales; at an integer scale its
+    // replication-aware form works from the feature maps like the fast kernel
+    const bool generic_rep = !h->fast_k2 && g.S > 0 && h->generic_rep;
+    const bool generic_needs_conf_up = !h->fast_k2 && !generic_rep;
     bool forked = false;
     auto resize_on = [&](cudaStream_t rs, const float *src, float *dst, int C, int layout) -> int {
         K1Params k1{};
@@ -662,7 +667,7 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     if (h->fast_k2) {
         CU(launch_k2_fast(k2, n, st, pdl && ingest));
     } else {
-        CU(launch_k2_generic(k2, n, st));
+        CU(generic_rep ? launch_k2_generic_rep(k2, n, st) : launch_k2_generic(k2, n, st));
     }
     h->launches += 1;
 

@@ -875,6 +875,107 @@ __global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic(const K2Params p
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2 generic path at an INTEGER scale (any kernel size <= 63, either border rule): the up-sampled map is the feature
+// map replicated S x S, so (a) the tile is staged straight from the feature maps - no materialised heat map is read -
+// and (b) the row pass, the expensive half for large kernels, is evaluated once per distinct FEATURE row under the
+// tile instead of once per image row (S times fewer).  The column pass then looks the image rows up through a small
+// row map (REFLECT_101 or zero border -> row of the row-pass result, or "zero").  Every smoothed value is produced by
+// the same IEEE operations on the same operands, in the same order, as k2_peaks_generic: results are identical.
+// Used for k = 19..63 at x8 (k = 25 is the fixed size of the reference's Python graph) and for the Python variant.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic_rep(const K2Params p)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int frame = blockIdx.z, part = blockIdx.y;
+    const int H = p.g.H, W = p.g.W, K = p.g.K, R = p.g.R, S = p.g.S, h = p.g.h, w = p.g.w;
+    const int tiles_x = (W + G_TX - 1) / G_TX;
+    const int x0 = (blockIdx.x % tiles_x) * G_TX, y0 = (blockIdx.x / tiles_x) * G_TY;
+    const int IW = G_TX + 2 + 2 * R, IH = G_TY + 2 + 2 * R; // image region: outputs + NMS halo + filter halo
+    const int TW = G_TX + 2;
+    const bool zero = p.border_zero != 0;
+    // distinct feature rows under the (border-mapped) image rows of the region
+    const int ylo = max(y0 - 1 - R, 0), yhi = min(y0 + G_TY + R, H - 1);
+    const int f_lo = ylo / S, nfr = yhi / S - f_lo + 1;
+    float *in = smem;               // [nfr][IW]   feature rows, columns already expanded and border-mapped
+    float *tmp = in + nfr * IW;     // [nfr+1][TW] row-pass result; row nfr is all zeros (rows beyond a zero border)
+    float *sm = tmp + (nfr + 1) * TW; // [G_TY+2][TW] smoothed
+    int *rowmap = reinterpret_cast<int *>(sm + (G_TY + 2) * TW); // [IH] image row of the region -> offset of its row in tmp
+    const float *plane = p.conf + ((size_t)frame * OPP_N_HEAT + part) * h * w;
+    for (int i = threadIdx.x; i < IH; i += blockDim.x) {
+        const int yy = y0 - 1 - R + i;
+        int m;
+        if (zero) {
+            m = (yy < 0 || yy >= H) ? nfr : yy / S - f_lo;
+        } else {
+            const int ry = clip_idx(reflect101(yy, H), H); // rows whose centre is outside the image are never used
+            m = min(max(ry / S - f_lo, 0), nfr - 1);
+        }
+        rowmap[i] = m * TW;
+    }
+    for (int c = threadIdx.x; c < TW; c += blockDim.x) tmp[nfr * TW + c] = 0.f;
+    int hot = 0;
+    for (int t = threadIdx.x; t < nfr * IW; t += blockDim.x) {
+        const int fr = t / IW, xx = x0 - 1 - R + t % IW;
+        float v;
+        if (zero && (xx < 0 || xx >= W)) {
+            v = 0.f;
+        } else {
+            const int rx = clip_idx(reflect101(xx, W), W);
+            v = __ldcg(plane + (size_t)(f_lo + fr) * w + rx / S);
+        }
+        in[t] = v;
+        hot |= v > p.skip_thresh;
+    }
+    // same exact early-out as the other peak kernels: the staged rows are everything the tile's pixels depend on
+    if (!__syncthreads_or(hot)) {
+        if (tile_done_is_last(p.cnt.k2_done + frame, gridDim.x * OPP_N_PARTS)) finalize_frame_peaks(p, frame, reinterpret_cast<int *>(smem));
+        return;
+    }
+    for (int t = threadIdx.x; t < nfr * TW; t += blockDim.x) {
+        const int r = t / TW, c = t % TW;
+        const float *q = in + r * IW + c; // q[j] = tap j of output column x0-1+c
+        float s;
+        if (K == 3 && !zero) {
+            s = __fadd_rn(__fmul_rn(q[R], p.taps[R]), __fmul_rn(__fadd_rn(q[R - 1], q[R + 1]), p.taps[R + 1]));
+        } else if (K == 5 && !zero) {
+            s = __fadd_rn(__fmul_rn(q[R], p.taps[R]), __fmul_rn(__fadd_rn(q[R - 1], q[R + 1]), p.taps[R + 1]));
+            s = __fadd_rn(s, __fmul_rn(__fadd_rn(q[R - 2], q[R + 2]), p.taps[R + 2]));
+        } else {
+            s = __fmul_rn(p.taps[0], q[0]);
+            for (int j = 1; j < K; ++j) s = __fadd_rn(s, __fmul_rn(p.taps[j], q[j]));
+        }
+        tmp[t] = s;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < (G_TY + 2) * TW; t += blockDim.x) {
+        const int r = t / TW, c = t % TW;
+        const int y = y0 - 1 + r, x = x0 - 1 + c;
+        float s = -CUDART_INF_F;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            const int *rm = rowmap + r + R; // rm[j] = offset in tmp of the row standing for image row y + j
+            const float *tc = tmp + c;
+            s = __fmul_rn(p.taps[R], tc[rm[0]]);
+            for (int j = 1; j <= R; ++j) s = __fadd_rn(s, __fmul_rn(p.taps[R + j], __fadd_rn(tc[rm[j]], tc[rm[-j]])));
+        }
+        sm[t] = s;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < G_TY * G_TX; t += blockDim.x) {
+        const int r = t / G_TX, c = t % G_TX;
+        const int y = y0 + r, x = x0 + c;
+        if (y >= H || x >= W) continue;
+        const float *q = sm + (r + 1) * TW + (c + 1);
+        const float s = q[0];
+        if (!(s > p.thresh)) continue;
+        float m = fmaxf(fmaxf(q[-TW - 1], q[-TW]), q[-TW + 1]);
+        m = fmaxf(m, fmaxf(fmaxf(q[-1], q[0]), q[1]));
+        m = fmaxf(m, fmaxf(fmaxf(q[TW - 1], q[TW]), q[TW + 1]));
+        if (s == m) emit_peak(p, frame, part, y, x);
+    }
+    if (tile_done_is_last(p.cnt.k2_done + frame, gridDim.x * OPP_N_PARTS)) finalize_frame_peaks(p, frame, reinterpret_cast<int *>(smem));
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: one CTA per (limb, frame): score all (a, b) peak pairs, order-preserving compaction of the
 // accepted candidates, std::sort-order sort, greedy matching.  The last limb of a frame to finish
 // assembles the frame's humans.
@@ -1796,6 +1897,23 @@ cudaError_t launch_k2_generic(const K2Params &p, int n_frames, cudaStream_t st)
     const int tiles = ((p.g.W + G_TX - 1) / G_TX) * ((p.g.H + G_TY - 1) / G_TY);
     dim3 grid(tiles, OPP_N_PARTS, n_frames);
     k2_peaks_generic<<<grid, OPP_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k2_generic_rep(const K2Params &p, int n_frames, cudaStream_t st)
+{
+    const int R = p.g.R, S = p.g.S;
+    if (S < 1) return cudaErrorInvalidValue;
+    const int IW = G_TX + 2 + 2 * R, IH = G_TY + 2 + 2 * R, TW = G_TX + 2;
+    const int nfr = (IH + S - 1) / S + 1; // most feature rows a region can touch
+    size_t smem = ((size_t)nfr * IW + (size_t)(nfr + 1) * TW + (size_t)(G_TY + 2) * TW) * sizeof(float) + (size_t)IH * sizeof(int);
+    if ((size_t)OPP_N_PARTS * p.capP * sizeof(int) > smem) smem = (size_t)OPP_N_PARTS * p.capP * sizeof(int);
+    int dyn_limit = 0;
+    BIG_SMEM_LIMIT(k2_peaks_generic_rep, dyn_limit);
+    if (smem > (size_t)dyn_limit) return cudaErrorInvalidValue;
+    const int tiles = ((p.g.W + G_TX - 1) / G_TX) * ((p.g.H + G_TY - 1) / G_TY);
+    dim3 grid(tiles, OPP_N_PARTS, n_frames);
+    k2_peaks_generic_rep<<<grid, OPP_THREADS, smem, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -100,6 +100,7 @@ size_t k2_fast_smem_bytes(const OppGeom &g, int tw, int th);
 bool k2_fast_supported(const OppGeom &g);
 cudaError_t launch_k2_fast(const K2Params &p, int n_frames, cudaStream_t st, bool pdl = false);
 cudaError_t launch_k2_generic(const K2Params &p, int n_frames, cudaStream_t st);
+cudaError_t launch_k2_generic_rep(const K2Params &p, int n_frames, cudaStream_t st); // integer scale: reads the feature maps
 cudaError_t launch_k3(const K3Params &p, int n_frames, size_t smem, cudaStream_t st, bool pdl = false);
 cudaError_t launch_k1(const K1Params &p, cudaStream_t st);
 cudaError_t launch_hwc_to_chw(const float *src, float *dst, int n, int C, int h, int w, cudaStream_t st);
