@@ -304,9 +304,21 @@ def main():
         eng._check(eng.L.opp_bench_latency(eng.h, C.byref(b), n_it, us.ctypes.data))
         return float(np.median(us[20:] if n_it > 40 else us)) * 1e-3
 
+    # pageable buffers in and out: what a caller of the reference's paf_processor contract passes (any host pointer)
+    def latency_p50_pageable():
+        c1, p1 = np.array(h_ring[0][0][:1]), np.array(h_ring[0][1][:1])
+        out = (np.zeros((1, eng.max_humans), capi.HUMAN_DT), np.zeros(1, np.int32), np.zeros(1, np.int32))
+        lat = []
+        for i in range(max(args.latency_iters, 1)):
+            t0 = time.perf_counter()
+            eng.process(c1, p1, out=out)
+            lat.append((time.perf_counter() - t0) * 1e3)
+        return statistics.median(lat[20:] if len(lat) > 40 else lat)
+
     barrier()
     lat_p50 = latency_p50()
     lat_p50_capi = latency_p50_capi()
+    lat_p50_pageable = latency_p50_pageable()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -440,6 +452,7 @@ def main():
             "latency_ms_p50": lat_p50,
             "latency_ms_p50_after_load": lat_p50_loaded,
             "latency_ms_p50_capi": lat_p50_capi,
+            "latency_ms_p50_pageable": lat_p50_pageable,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k2_peaks_fast<8,8,STORE> (resize of the 19+38 maps fused into smooth + NMS + peak list)",
                          "achieved": k2s_gbs, "peak": peak, "unit": "GB/s", "frac": k2s_gbs / peak, "traffic": ncu_traffic("r1_final_k2store_ncu_raw.csv"),

@@ -52,6 +52,8 @@ struct Slot {
     // pinned results
     opp_human_t *h_humans = nullptr;
     int *h_n_humans = nullptr, *h_flags = nullptr;
+    float *h_in_conf = nullptr, *h_in_paf = nullptr; // pinned staging for a few pageable input frames (allocated on first use)
+    float *d_in_conf = nullptr, *d_in_paf = nullptr; // their device-visible aliases
     int *h_done = nullptr;      // pinned completion word written by the assembly kernel (latency path)
     int done_tag = 0;           // value that word takes when the batch in flight is complete; 0 = wait on the event
     bool ms_pending = false;    // last_ms not read from the events yet
@@ -95,6 +97,7 @@ struct opp_handle_s {
     bool done_flag = true; // completion word in pinned memory on the latency path (OPP_NO_DONE_FLAG=1 disables)
     int tag_seq = 0;
     bool generic_rep = true; // integer scales outside the fast kernel's range: replication-aware generic kernel (OPP_NO_GENERIC_REP=1: via the materialised map)
+    bool stage_pageable = true; // latency path for pageable inputs through pinned staging (OPP_NO_STAGE_PAGEABLE=1: cudaMemcpyAsync from pageable memory)
     bool pdl = true; // programmatic dependent launch on the latency path (OPP_NO_PDL=1 disables)
     int zero_copy_in_max = 0; // kernels reading pinned host maps in place: measured slower than staging them (kept for experiments)
     int ingest_max = 4;       // up to this many frames, pinned host maps are pulled in by one kernel instead of memset + 2 DMA copies
@@ -228,6 +231,7 @@ int free_slot(opp_handle_s *h, Slot &s)
     cudaFree(s.d_pk_key), cudaFree(s.d_peaks), cudaFree(s.d_part_ofs), cudaFree(s.d_conns), cudaFree(s.d_n_conns);
     cudaFree(s.d_cand), cudaFree(s.d_humans), cudaFree(s.d_n_humans), cudaFree(s.d_href_parts), cudaFree(s.d_times);
     cudaFreeHost(s.h_humans), cudaFreeHost(s.h_n_humans), cudaFreeHost(s.h_flags), cudaFreeHost(s.h_done);
+    cudaFreeHost(s.h_in_conf), cudaFreeHost(s.h_in_paf);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
@@ -506,6 +510,7 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
         h->k2_skip = getenv("OPP_K2_NOSKIP") == nullptr;
         h->zero_copy_out = getenv("OPP_NO_ZEROCOPY_OUT") == nullptr;
         h->pdl = getenv("OPP_NO_PDL") == nullptr;
+        h->stage_pageable = getenv("OPP_NO_STAGE_PAGEABLE") == nullptr;
         h->generic_rep = getenv("OPP_NO_GENERIC_REP") == nullptr;
         h->done_flag = getenv("OPP_NO_DONE_FLAG") == nullptr;
         h->paf_early = getenv("OPP_NO_PAF_EARLY") == nullptr;
@@ -547,7 +552,25 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     const size_t hw = (size_t)g.h * g.w, HW = (size_t)g.H * g.W;
     cudaStream_t st = s.stream;
     CU(cudaEventRecord(s.ev_start, st));
-    const bool ingest = b.in_mem == OPP_MEM_HOST && b.in_layout == OPP_LAYOUT_CHW && n <= h->ingest_max && mapped_host(b.conf) && mapped_host(b.paf);
+    // A few frames in host memory take the latency path.  Pinned buffers are read in place; PAGEABLE ones (what a
+    // caller of the reference's paf_processor passes) are first copied by this thread into the slot's pinned staging:
+    // the heat maps now, the PAFs - which only the limb kernel reads - after ingest and peak kernel have been launched,
+    // so that two thirds of the copy overlap with GPU work instead of preceding it.
+    const bool few_host = b.in_mem == OPP_MEM_HOST && b.in_layout == OPP_LAYOUT_CHW && n <= h->ingest_max;
+    const float *m_conf = few_host ? (const float *)mapped_host(b.conf) : nullptr, *m_paf = few_host ? (const float *)mapped_host(b.paf) : nullptr;
+    bool late_paf_copy = false;
+    if (few_host && !(m_conf && m_paf) && h->stage_pageable) {
+        if (!s.h_in_conf) {
+            CU(cudaMallocHost(&s.h_in_conf, (size_t)h->ingest_max * OPP_N_HEAT * hw * sizeof(float)));
+            CU(cudaMallocHost(&s.h_in_paf, (size_t)h->ingest_max * OPP_N_PAF * hw * sizeof(float)));
+            CU(cudaHostGetDevicePointer((void **)&s.d_in_conf, s.h_in_conf, 0));
+            CU(cudaHostGetDevicePointer((void **)&s.d_in_paf, s.h_in_paf, 0));
+        }
+        std::memcpy(s.h_in_conf, b.conf, (size_t)n * OPP_N_HEAT * hw * sizeof(float));
+        m_conf = s.d_in_conf, m_paf = s.d_in_paf;
+        late_paf_copy = true;
+    }
+    const bool ingest = few_host && m_conf && m_paf;
     // (the limb kernel can only be scheduled early when no up-sampled maps are written on a side stream in between)
     const bool paf_early = ingest && h->pdl && h->paf_early && h->fast_k2 && h->k3_plan.paf_in_smem && !h->trace && !b.conf_up && !b.paf_up;
     if (!ingest) CU(cudaMemsetAsync(s.d_counters, 0, h->counters_ints * sizeof(int), st));
@@ -572,15 +595,19 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
         h->launches += 2;
         conf = s.d_conf, paf = s.d_paf;
     } else if (ingest && paf_early) {
+        // (pageable PAFs: copied into the staging buffer just before the limb kernel is launched, see below)
         // only the heat maps (and the counter reset) go through the ingest kernel; the limb kernel, scheduled early by
         // programmatic dependent launch, pulls each limb's PAF tile from the pinned buffer while the peak kernel runs
-        CU(launch_ingest((const float *)mapped_host(b.conf), s.d_conf, (size_t)n * OPP_N_HEAT * hw, nullptr, nullptr, 0, s.d_counters,
-                         (int)h->counters_ints, st));
+        CU(launch_ingest(m_conf, s.d_conf, (size_t)n * OPP_N_HEAT * hw, nullptr, nullptr, 0, s.d_counters, (int)h->counters_ints, st));
         h->launches += 1;
-        conf = s.d_conf, paf = (const float *)mapped_host(b.paf);
+        conf = s.d_conf, paf = m_paf;
     } else if (ingest) {
-        CU(launch_ingest((const float *)mapped_host(b.conf), s.d_conf, (size_t)n * OPP_N_HEAT * hw, (const float *)mapped_host(b.paf), s.d_paf,
-                         (size_t)n * OPP_N_PAF * hw, s.d_counters, (int)h->counters_ints, st));
+        if (late_paf_copy) { // the PAFs go through the ingest kernel here: they must be staged first
+            std::memcpy(s.h_in_paf, b.paf, (size_t)n * OPP_N_PAF * hw * sizeof(float));
+            late_paf_copy = false;
+        }
+        CU(launch_ingest(m_conf, s.d_conf, (size_t)n * OPP_N_HEAT * hw, m_paf, s.d_paf, (size_t)n * OPP_N_PAF * hw, s.d_counters,
+                         (int)h->counters_ints, st));
         h->launches += 1;
         conf = s.d_conf, paf = s.d_paf;
     } else if (b.in_mem == OPP_MEM_HOST && n <= h->zero_copy_in_max && mapped_host(b.conf) && mapped_host(b.paf)) {
@@ -714,6 +741,7 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     k3.paf_early = paf_early;
     k3.true_index = c.variant == OPP_VARIANT_PYTHON;
     k3.thr_vec = 0.05f, k3.thr_human = 0.4f; // THRESH_VECTOR_SCORE, THRESH_HUMAN_SCORE, src/paf.cpp:61,64
+    if (late_paf_copy) std::memcpy(s.h_in_paf, b.paf, (size_t)n * OPP_N_PAF * hw * sizeof(float)); // while ingest + peak kernel run
     CU(launch_k3(k3, n, h->k3_smem, st, pdl && h->fast_k2));
     h->launches += 1;
 

@@ -40,6 +40,8 @@ out.append("| p50 latency, 1 frame, pinned host buffers, through the Python engi
            % (b["latency_ms_p50"], b.get("latency_ms_p50_after_load", float("nan"))))
 if "latency_ms_p50_capi" in b:
     out.append("| the same call looped from C (`opp_bench_latency`) | %.4f ms |" % b["latency_ms_p50_capi"])
+if "latency_ms_p50_pageable" in b:
+    out.append("| the same call with pageable buffers in and out (the reference's contract: any host pointer) | %.4f ms |" % b["latency_ms_p50_pageable"])
 out.append("| roofline, dominant kernel of the materialised step (peaks + resize fused) | %.0f GB/s = %.3f of measured %.1f GB/s; ncu traffic %.3f GB vs %.3f GB algorithmic |"
            % (b["roofline"]["achieved"], b["roofline"]["frac"], b["roofline"]["peak"], (b["roofline"].get("traffic") or 0) / 1e9, b["roofline"]["algorithmic_bytes_per_launch"] / 1e9))
 out.append("| stand-alone resize kernel | %.0f GB/s = %.3f |" % (b["roofline_k1"]["achieved"], b["roofline_k1"]["frac"]))

@@ -16,7 +16,7 @@ cap() { # name, demangled-name regex, launches of that kernel to skip first
     ls -la gpurun_out/prof_$1.ncu-rep
 }
 [ "${ONLY_K2:-0}" != 1 ] && cap k2store 'k2_peaks_fast<\(int\)8, \(int\)8, \(bool\)1>'
-cap k2 'k2_peaks_fast<\(int\)8, \(int\)8, \(bool\)0>' 16   # past the one-frame launches of the two latency loops (Python and C, 8 calls each): a 64-frame launch
+cap k2 'k2_peaks_fast<\(int\)8, \(int\)8, \(bool\)0>' 24   # past the one-frame launches of the three latency loops (8 calls each): a 64-frame launch
 if [ "${ONLY_K2:-0}" != 1 ]; then
 cap k1 'k1_replicate_chw'
 cap k3 'k3_limbs'
