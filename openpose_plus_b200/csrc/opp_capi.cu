@@ -205,6 +205,7 @@ void plan_k3_smem(opp_handle_s *h)
     if (p.cand_in_smem) off += align_up(cand_bytes, 16);
     p.off_used = (int)off, off += align_up(2 * (size_t)capP, 16);
     p.off_misc = (int)off, off += 64;
+    p.off_keys = (int)off, off += align_up(2 * (size_t)capP * sizeof(int), 16); // unordered keys of the limb's two parts
     const size_t phase1 = off;
     // assembly phase (re-uses the same bytes): partial humans, survivors, connections, peak x/y/score
     off = 0;
@@ -702,6 +703,7 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     // ---- limbs, matching, assembly
     K3Params k3 = h->k3_plan;
     k3.g = g, k3.paf = paf, k3.peaks = s.d_peaks, k3.part_ofs = s.d_part_ofs;
+    k3.pk_key = s.d_pk_key, k3.conf = conf, k3.conf_up = conf_up_for_k2;
     k3.capP = c.max_peaks_per_part, k3.capC = c.max_cands_per_limb, k3.capH = c.max_humans;
     k3.cnt = k2.cnt;
     k3.cand_scratch = s.d_cand, k3.conns = s.d_conns, k3.n_conns = s.d_n_conns;

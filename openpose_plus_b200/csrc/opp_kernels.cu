@@ -34,6 +34,8 @@ namespace
 __constant__ int c_pair_a[OPP_N_PAIRS] = {1, 1, 2, 3, 5, 6, 1, 8, 9, 1, 11, 12, 1, 0, 14, 0, 15, 2, 5};
 __constant__ int c_pair_b[OPP_N_PAIRS] = {2, 5, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 0, 14, 16, 15, 17, 16, 17};
 __constant__ int c_net_x[OPP_N_PAIRS] = {12, 20, 14, 16, 22, 24, 0, 2, 4, 6, 8, 10, 28, 30, 34, 32, 36, 18, 26};
+// first limb whose (a, b) contains the part: that limb's CTA writes the part's slice of all_peaks
+__constant__ int c_part_writer[OPP_N_PARTS] = {12, 0, 0, 2, 3, 1, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 14, 16};
 
 __device__ __forceinline__ int reflect101(int p, int n)
 {
@@ -349,57 +351,39 @@ __global__ void __launch_bounds__(OPP_THREADS) k0_hwc_to_chw(const float *src, f
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 shared tail: the last tile of a frame turns the unordered per-part key lists into the
-// reference's all_peaks vector (raster order k -> y -> x, ids = running index).
+// The peak kernels leave one unordered list of keys (y * W + x) per (frame, part).  The reference's all_peaks vector
+// is those peaks in raster order part -> y -> x with the running index as id (src/post-process.h:176-199): a peak's
+// rank inside its part's list plus the sizes of the parts before it.  The limb kernel's CTAs establish that order,
+// each for the two parts of its limb (every part belongs to at least one limb): order_part_peaks ranks one part's
+// keys (staged in shared memory), hands the (x, y) of every peak to the caller in raster order and - in the first limb
+// that contains the part (c_part_writer) - writes the part's slice of the global all_peaks array.
 // ------------------------------------------------------------------------------------------------
-__device__ void finalize_frame_peaks(const K2Params &p, int frame, int *s_keys /* >= 18*capP ints */)
+struct PeakSource {
+    OppGeom g;
+    const float *conf;    // [n,19,h,w] feature maps: score = up-sampled, unsmoothed value at the peak (src/post-process.h:192)
+    const float *conf_up; // materialised [n,19,H,W] map when the geometry has no closed form (non-integer scale)
+};
+
+__device__ __forceinline__ void order_part_peaks(const PeakSource &src, int frame, int part, const int *s_keys, int n, int ofs, int2 *s_xy,
+                                                 opp_peak_t *out /* frame's all_peaks, or nullptr: another limb writes this part's slice */)
 {
-    const int W = p.g.W, H = p.g.H;
-    const int capP = p.capP;
-    __shared__ int s_n[OPP_N_PARTS], s_ofs[OPP_N_PARTS + 1];
-    int over = 0;
-    if (threadIdx.x < OPP_N_PARTS) {
-        const int raw = __ldcg(p.cnt.pk_cnt + frame * OPP_N_PARTS + threadIdx.x);
-        s_n[threadIdx.x] = min(raw, capP);
-        over = raw > capP;
-    }
-    over = __syncthreads_or(over);
-    if (threadIdx.x == 0) {
-        int ofs = 0;
-        for (int part = 0; part < OPP_N_PARTS; ++part) s_ofs[part] = ofs, ofs += s_n[part];
-        s_ofs[OPP_N_PARTS] = ofs;
-    }
-    __syncthreads();
-    // all keys of the frame in ONE round trip: flat index over the parts' lists
-    const int total = s_ofs[OPP_N_PARTS];
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
-        int part = 0;
-        while (part + 1 < OPP_N_PARTS && s_ofs[part + 1] <= t) ++part;
-        s_keys[t] = __ldcg(p.pk_key + ((size_t)frame * OPP_N_PARTS + part) * capP + (t - s_ofs[part]));
-    }
-    __syncthreads();
-    // rank inside the part = raster order; one more round trip for the scores
-    opp_peak_t *out = p.peaks + (size_t)frame * OPP_N_PARTS * capP;
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
-        int part = 0;
-        while (part + 1 < OPP_N_PARTS && s_ofs[part + 1] <= t) ++part;
-        const int ofs = s_ofs[part], n = s_ofs[part + 1] - ofs;
-        const int *k = s_keys + ofs;
+    const int W = src.g.W, H = src.g.H;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
         const int key = s_keys[t];
         int rank = 0;
-        for (int u = 0; u < n; ++u) rank += (k[u] < key);
+        for (int u = 0; u < n; ++u) rank += (s_keys[u] < key);
         const int y = key / W, x = key - y * W;
+        s_xy[rank] = make_int2(x, y);
+        if (!out) continue;
         float score;
-        if (p.conf_up)
-            score = __ldcg(p.conf_up + ((size_t)frame * OPP_N_HEAT + part) * H * W + key);
+        if (src.conf_up)
+            score = __ldcg(src.conf_up + ((size_t)frame * OPP_N_HEAT + part) * H * W + key);
         else
-            score = upsample_at(p.g, p.conf + ((size_t)frame * OPP_N_HEAT + part) * p.g.h * p.g.w, y, x);
+            score = upsample_at(src.g, src.conf + ((size_t)frame * OPP_N_HEAT + part) * src.g.h * src.g.w, y, x);
         opp_peak_t pk;
         pk.part_id = part, pk.x = x, pk.y = y, pk.score = score, pk.id = ofs + rank;
         out[ofs + rank] = pk;
     }
-    if (threadIdx.x <= OPP_N_PARTS) p.part_ofs[frame * (OPP_N_PARTS + 1) + threadIdx.x] = s_ofs[threadIdx.x];
-    if (threadIdx.x == 0 && over) atomicOr(p.flags + frame, OPP_FLAG_PEAK_OVERFLOW);
 }
 
 __device__ __forceinline__ bool tile_done_is_last(int *counter, int total)
@@ -801,11 +785,9 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
 
     if (STORE) store_units(st_total);
     stamp2(p, 4);
-    if (tile_done_is_last(p.cnt.k2_done + frame, p.nxs * p.nys * OPP_N_PARTS)) {
-        stamp2(p, 5);
-        finalize_frame_peaks(p, frame, reinterpret_cast<int *>(smem));
-        stamp2(p, 6);
-    }
+    // No tail: the unordered key lists are put into the reference's raster order by the limb kernel's CTAs, each
+    // for its own two parts (order_part_peaks).  A per-frame "last tile" epilogue here kept every CTA - and its shared
+    // memory - waiting a microsecond for the answer of its done-counter atomic (a third of all stall samples).
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -844,7 +826,6 @@ __global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic(const K2Params p
     // Same exact early-out as the fast kernel: the staged region is everything the tile's smoothed
     // pixels depend on; if all of it is <= thresh * (1 - 2^-13) no pixel of the tile can be a peak.
     if (!__syncthreads_or(hot)) {
-        if (tile_done_is_last(p.cnt.k2_done + frame, gridDim.x * OPP_N_PARTS)) finalize_frame_peaks(p, frame, reinterpret_cast<int *>(smem));
         return;
     }
     for (int t = threadIdx.x; t < IH * TW; t += blockDim.x) {
@@ -889,7 +870,6 @@ __global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic(const K2Params p
         m = fmaxf(m, fmaxf(fmaxf(q[TW - 1], q[TW]), q[TW + 1]));
         if (s == m) emit_peak(p, frame, part, y, x);
     }
-    if (tile_done_is_last(p.cnt.k2_done + frame, gridDim.x * OPP_N_PARTS)) finalize_frame_peaks(p, frame, reinterpret_cast<int *>(smem));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -946,7 +926,6 @@ __global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic_rep(const K2Para
     }
     // same exact early-out as the other peak kernels: the staged rows are everything the tile's pixels depend on
     if (!__syncthreads_or(hot)) {
-        if (tile_done_is_last(p.cnt.k2_done + frame, gridDim.x * OPP_N_PARTS)) finalize_frame_peaks(p, frame, reinterpret_cast<int *>(smem));
         return;
     }
     for (int t = threadIdx.x; t < nfr * TW; t += blockDim.x) {
@@ -990,7 +969,6 @@ __global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic_rep(const K2Para
         m = fmaxf(m, fmaxf(fmaxf(q[TW - 1], q[TW]), q[TW + 1]));
         if (s == m) emit_peak(p, frame, part, y, x);
     }
-    if (tile_done_is_last(p.cnt.k2_done + frame, gridDim.x * OPP_N_PARTS)) finalize_frame_peaks(p, frame, reinterpret_cast<int *>(smem));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1172,7 +1150,7 @@ __device__ __forceinline__ void stamp(const K3Params &p, int frame, int pair_id,
 // finished last.  Everything it needs (connection counts, all connections, peak x/y/score) is staged
 // into shared memory in two parallel round trips; the order-dependent part then runs in one warp
 // without touching global memory, and the output is written by the whole CTA.
-__device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem_raw)
+__device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem_raw, const int *pofs /* shared: 19 part offsets */)
 {
     int *hr = reinterpret_cast<int *>(smem_raw + p.off_href);                   // [capH][21]
     int2 *s_pk = reinterpret_cast<int2 *>(smem_raw + p.off_score);              // [n_peaks] {x | y << 16, score bits} (score_in_smem)
@@ -1181,9 +1159,9 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
     __shared__ int s_state[8];                                                  // n, -, flags, merges, n_out
     __shared__ int s_nc[OPP_N_PAIRS], s_coff[OPP_N_PAIRS + 1];
     const int capH = p.capH, capP = p.capP;
-    const int *pofs = p.part_ofs + frame * (OPP_N_PARTS + 1);
-    const int n_peaks = __ldcg(pofs + OPP_N_PARTS);
+    const int n_peaks = pofs[OPP_N_PARTS];
     const opp_peak_t *peaks = p.peaks + (size_t)frame * OPP_N_PARTS * capP;
+    if (threadIdx.x <= OPP_N_PARTS) p.part_ofs[frame * (OPP_N_PARTS + 1) + threadIdx.x] = pofs[threadIdx.x]; // for opp_debug_fetch
     const bool all_conns = p.conns_in_smem != 0, pk_smem = p.score_in_smem != 0;
     if (threadIdx.x < 32) { // connection counts of the 19 limbs and their exclusive prefix sums, one warp scan
         const int ln = threadIdx.x;
@@ -1209,7 +1187,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
     __shared__ unsigned char s_pa[OPP_N_PAIRS], s_pb[OPP_N_PAIRS]; // c_pair_a / c_pair_b for lane-divergent limb indices
     if (threadIdx.x >= 96 && threadIdx.x < 96 + OPP_N_PAIRS) s_pa[threadIdx.x - 96] = (unsigned char)c_pair_a[threadIdx.x - 96], s_pb[threadIdx.x - 96] = (unsigned char)c_pair_b[threadIdx.x - 96];
     const bool use_owner = p.owner_in_smem != 0 && all_conns;
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + OPP_N_PARTS + 1) s_pofs[threadIdx.x - 64] = __ldcg(pofs + threadIdx.x - 64);
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + OPP_N_PARTS + 1) s_pofs[threadIdx.x - 64] = pofs[threadIdx.x - 64];
     if (use_owner) {
         for (int t = threadIdx.x; t < 17 * capP; t += blockDim.x) s_c1[t] = 0xffff;
         for (int t = threadIdx.x; t < (OPP_N_PARTS * capP + 31) / 32; t += blockDim.x) s_in[t] = 0u;
@@ -1611,7 +1589,6 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int h = p.g.h, w = p.g.w, capP = p.capP, capC = p.capC;
     const int pa = c_pair_a[pair_id], pb = c_pair_b[pair_id], cx = c_net_x[pair_id]; // the y channel is the next plane
-    const int *pofs = p.part_ofs + frame * (OPP_N_PARTS + 1);
     float *s_paf = reinterpret_cast<float *>(smem_raw + p.off_paf);      // [2][h*w]
     __shared__ unsigned long long s_mbar;
     bool paf_bulk = false;
@@ -1633,9 +1610,25 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
     const bool paf_early = p.paf_early && p.paf_in_smem;
     if (paf_early) fetch_paf_tile();
     pdl_wait(); // peaks come from the peak kernel, which may still be running when this CTA is scheduled
-    const int ofs_a = __ldcg(pofs + pa), na = __ldcg(pofs + pa + 1) - ofs_a;
-    const int ofs_b = __ldcg(pofs + pb), nb = __ldcg(pofs + pb + 1) - ofs_b;
-    const opp_peak_t *peaks = p.peaks + (size_t)frame * OPP_N_PARTS * capP;
+    // sizes of the 18 key lists -> part offsets in all_peaks (one warp scan)
+    __shared__ int s_pcnt[OPP_N_PARTS], s_pofs3[OPP_N_PARTS + 1];
+    if (tid < 32) {
+        const int raw = tid < OPP_N_PARTS ? __ldcg(p.cnt.pk_cnt + frame * OPP_N_PARTS + tid) : 0;
+        const int cnt = min(raw, capP);
+        if (raw > capP && (tid == pa || tid == pb)) atomicOr(p.flags + frame, OPP_FLAG_PEAK_OVERFLOW);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += v;
+        }
+        if (tid < OPP_N_PARTS) s_pcnt[tid] = cnt, s_pofs3[tid + 1] = incl;
+        if (tid == 0) s_pofs3[0] = 0;
+    }
+    __syncthreads();
+    const int ofs_a = s_pofs3[pa], na = s_pcnt[pa];
+    const int ofs_b = s_pofs3[pb], nb = s_pcnt[pb];
+    opp_peak_t *peaks = p.peaks + (size_t)frame * OPP_N_PARTS * capP;
 
     int2 *s_pa = reinterpret_cast<int2 *>(smem_raw + p.off_pk);          // [capP]
     int2 *s_pb = s_pa + capP;                                            // [capP]
@@ -1651,6 +1644,18 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
     }
 
     stamp(p, frame, pair_id, 0);
+    // this limb's two parts: keys -> raster order (all_peaks slices in global memory, (x, y) lists in shared memory)
+    {
+        int *s_ka = reinterpret_cast<int *>(smem_raw + p.off_keys), *s_kb = s_ka + capP;
+        const int *ga = p.pk_key + ((size_t)frame * OPP_N_PARTS + pa) * capP, *gb = p.pk_key + ((size_t)frame * OPP_N_PARTS + pb) * capP;
+        for (int t = tid; t < na; t += blockDim.x) s_ka[t] = __ldcg(ga + t);
+        for (int t = tid; t < nb; t += blockDim.x) s_kb[t] = __ldcg(gb + t);
+        __syncthreads();
+        PeakSource src;
+        src.g = p.g, src.conf = p.conf, src.conf_up = p.conf_up;
+        order_part_peaks(src, frame, pa, s_ka, na, ofs_a, s_pa, c_part_writer[pa] == pair_id ? peaks : nullptr);
+        order_part_peaks(src, frame, pb, s_kb, nb, ofs_b, s_pb, c_part_writer[pb] == pair_id ? peaks : nullptr);
+    }
     int n_cand = 0;
     const long n_pairs = (long)na * nb;
     if (n_pairs > 0) {
@@ -1660,8 +1665,6 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
             if (!paf_early) fetch_paf_tile();
             px_plane = s_paf, py_plane = s_paf + h * w;
         }
-        for (int t = tid; t < na; t += blockDim.x) s_pa[t] = make_int2(__ldcg(&peaks[ofs_a + t].x), __ldcg(&peaks[ofs_a + t].y));
-        for (int t = tid; t < nb; t += blockDim.x) s_pb[t] = make_int2(__ldcg(&peaks[ofs_b + t].x), __ldcg(&peaks[ofs_b + t].y));
         for (int t = tid; t < 2 * capP; t += blockDim.x) s_used[t] = 0;
         if (tid < 16) s_misc[tid] = 0;
         stage_wait();
@@ -1803,7 +1806,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
     stamp(p, frame, pair_id, 4);
     if (tile_done_is_last(p.cnt.k3_done + frame, OPP_N_PAIRS)) {
         stamp(p, frame, pair_id, 5);
-        assemble_frame(p, frame, smem_raw);
+        assemble_frame(p, frame, smem_raw, s_pofs3);
         stamp(p, frame, pair_id, 9);
     }
 }

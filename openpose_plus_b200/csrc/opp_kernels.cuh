@@ -56,8 +56,12 @@ struct K2Params {
 struct K3Params {
     OppGeom g;
     const float *paf; // [n,38,h,w]
-    const opp_peak_t *peaks;
-    const int *part_ofs;
+    // peaks: the peak kernel's unordered keys in, the reference's all_peaks (raster order, ids) out
+    const int *pk_key;      // [n][18][capP] y*W+x, unordered
+    const float *conf;      // [n,19,h,w] feature maps (peak scores)
+    const float *conf_up;   // [n,19,H,W] materialised map, only at non-integer scales
+    opp_peak_t *peaks;      // [n][18*capP] written by this kernel
+    int *part_ofs;          // [n][19]      written by this kernel
     int capP, capC, capH;
     OppCounters cnt;
     float *cand_scratch;   // [n][19][2][capC][3] when candidates do not fit shared memory
@@ -71,7 +75,7 @@ struct K3Params {
     int *stats;            // [n][4] partial humans, merges, total candidates, total pairs
     int paf_in_smem, cand_in_smem, score_in_smem, conns_in_smem, owner_in_smem;
     // shared-memory carve-up (byte offsets)
-    int off_paf, off_pk, off_cand, off_used, off_misc, off_href, off_score, off_conn, off_keep, off_owner;
+    int off_paf, off_pk, off_cand, off_used, off_misc, off_keys, off_href, off_score, off_conn, off_keep, off_owner;
     float thr_vec, thr_human;
     // completion word for the latency path: every frame's assembly bumps batch_done; the one that completes the batch
     // writes done_tag to host_done (mapped pinned memory) after a system-scope fence, so the host can spin on it
