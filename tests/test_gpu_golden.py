@@ -292,6 +292,24 @@ def test_latency_path_pipelined_single_frames(mods, monkeypatch):
 
     run(True)
     run(False)
+    # pinned buffers that are only 4-byte aligned: the scalar ingest and the cp.async form of the PAF tile fetch
+    raw_c, raw_p = capi.pinned_empty((conf[0].size + 1,), np.float32), capi.pinned_empty((paf[0].size + 1,), np.float32)
+    oc, op = raw_c[1:].reshape(conf[:1].shape), raw_p[1:].reshape(paf[:1].shape)
+    assert oc.ctypes.data % 16 == 4
+    eng = Engine(46, 54, max_batch=1)
+    for f in (0, 5):
+        oc[...] = conf[f]
+        op[...] = paf[f]
+        h, c, fl = eng.process(oc, op)
+        assert c[0] == want_c[f] and H.humans_equal(h[0, :c[0]], want_h[f, :want_c[f]]) is None, f
+    eng.close()
+    # plain numpy (pageable) inputs: staged through the slot's pinned buffers, PAFs copied while the GPU already works
+    eng = Engine(46, 54, max_batch=4)
+    for f in (1, 7):
+        h, c, fl = eng.process(conf[f:f + 3], paf[f:f + 3])
+        for k in range(3):
+            assert c[k] == want_c[f + k] and H.humans_equal(h[k, :c[k]], want_h[f + k, :want_c[f + k]]) is None, (f, k)
+    eng.close()
     for switch in ("OPP_NO_PDL", "OPP_NO_PAF_EARLY", "OPP_NO_DONE_FLAG"):
         monkeypatch.setenv(switch, "1")
         run(True)
