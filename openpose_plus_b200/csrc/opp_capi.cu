@@ -874,8 +874,8 @@ int opp_wait(opp_handle_t h, int ticket)
                     if (t2[cta * 8 + k] > mx[k]) mx[k] = t2[cta * 8 + k];
             }
             fprintf(stderr, "[opp k2] %d CTAs, latest stamp per phase (us after first CTA start):", nct);
-            for (int k = 0; k < 7; ++k) fprintf(stderr, " %6.1f", mx[k] ? (double)(mx[k] - b0) * 1e-3 : -1.0);
-            fprintf(stderr, "  (start staged analysed row-pass columns | last: entered finalized)\n");
+            for (int k = 0; k < 5; ++k) fprintf(stderr, " %6.1f", mx[k] ? (double)(mx[k] - b0) * 1e-3 : -1.0);
+            fprintf(stderr, "  (start staged analysed row-pass columns)\n");
             cudaMemset(d2, 0, sizeof t2);
         }
         fprintf(stderr, "[opp trace] ticket %d n=%d start %.3f | k1 %.3f-%.3f | k2 %.3f-%.3f | k3 -%.3f | copies -%.3f | done %.3f (ms)\n", s.ticket,

@@ -27,7 +27,7 @@ struct OppGeom {
 // frame-level counters, cleared by one memset per batch
 struct OppCounters {
     int *pk_cnt;  // [n][18] peaks appended per (frame, part)
-    int *k2_done; // [n]     tiles of the frame that finished peak detection
+    int *k2_done; // [n]     unused since the peak kernels have no per-frame epilogue (kept for the counter layout)
     int *k3_done; // [n]     limbs of the frame that finished matching
 };
 
