@@ -1610,6 +1610,13 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
     const bool paf_early = p.paf_early && p.paf_in_smem;
     if (paf_early) fetch_paf_tile();
     pdl_wait(); // peaks come from the peak kernel, which may still be running when this CTA is scheduled
+    // The two key lists of this limb are fetched whole (capP entries each; those beyond the list's size are ignored)
+    // in the same round trip as the list sizes, instead of after them.
+    int *s_ka = reinterpret_cast<int *>(smem_raw + p.off_keys), *s_kb = s_ka + capP;
+    for (int t = tid; t < 2 * capP; t += blockDim.x) {
+        const int part = t < capP ? pa : pb, k = t < capP ? t : t - capP;
+        s_ka[t] = __ldcg(p.pk_key + ((size_t)frame * OPP_N_PARTS + part) * capP + k);
+    }
     // sizes of the 18 key lists -> part offsets in all_peaks (one warp scan)
     __shared__ int s_pcnt[OPP_N_PARTS], s_pofs3[OPP_N_PARTS + 1];
     if (tid < 32) {
@@ -1646,11 +1653,6 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
     stamp(p, frame, pair_id, 0);
     // this limb's two parts: keys -> raster order (all_peaks slices in global memory, (x, y) lists in shared memory)
     {
-        int *s_ka = reinterpret_cast<int *>(smem_raw + p.off_keys), *s_kb = s_ka + capP;
-        const int *ga = p.pk_key + ((size_t)frame * OPP_N_PARTS + pa) * capP, *gb = p.pk_key + ((size_t)frame * OPP_N_PARTS + pb) * capP;
-        for (int t = tid; t < na; t += blockDim.x) s_ka[t] = __ldcg(ga + t);
-        for (int t = tid; t < nb; t += blockDim.x) s_kb[t] = __ldcg(gb + t);
-        __syncthreads();
         PeakSource src;
         src.g = p.g, src.conf = p.conf, src.conf_up = p.conf_up;
         order_part_peaks(src, frame, pa, s_ka, na, ofs_a, s_pa, c_part_writer[pa] == pair_id ? peaks : nullptr);
