@@ -39,6 +39,28 @@ def test_cuda_reproduces_reference_golden(mods, path):
         assert np.array_equal(eng.debug_parts(t, 0, i), g["hrefs"]["parts"][i])
 
 
+def test_cuda_reproduces_python_variant_vectors(mods):
+    """OPP_VARIANT_PYTHON against its committed regression vectors (oracle variant 1; unpinned, see
+    scripts/make_golden_python_variant.py): peaks, connections, humans and person -> part ids, byte for byte."""
+    Engine, capi, H = mods
+    paths = sorted(glob.glob(os.path.join(GOLD, "pyvariant_*.npz")))
+    assert len(paths) >= 2
+    for path in paths:
+        g = np.load(path)
+        h, w, oh, ow, k = [int(v) for v in g["geom"]]
+        eng = Engine(h, w, oh, ow, k, max_batch=1, max_peaks_per_part=512, max_cands_per_limb=8192, max_humans=512, variant=capi.VARIANT_PYTHON)
+        t = eng.submit(g["conf"][None], g["paf"][None])
+        humans, counts, flags = eng.wait(t)
+        assert flags[0] == 0
+        assert np.array_equal(eng.debug_peaks(t, 0, cap=18 * 512).view(np.uint8), g["peaks"].view(np.uint8))
+        for p in range(19):
+            assert np.array_equal(eng.debug_conns(t, 0, p).view(np.uint8), g["conns_%02d" % p].view(np.uint8)), p
+        assert H.humans_equal(humans[0, :counts[0]], g["humans"]) is None
+        for i in range(counts[0]):
+            assert np.array_equal(eng.debug_parts(t, 0, i), g["hrefs"]["parts"][i])
+        eng.close()
+
+
 def test_materialised_maps_and_layouts(mods):
     import torch
     from oracle.oracle import Oracle

@@ -139,3 +139,16 @@ def test_python_path_grouping_indexes_by_position():
     o0, o1 = Oracle(46, 54, 368, 432, 17), Oracle(46, 54, 368, 432, 17)
     o1.L.orc_set_variant(o1.ctx, 0)
     assert o0.run(c, p)["n_humans"] == o1.run(c, p)["n_humans"]
+
+
+def test_python_variant_oracle_reproduces_its_vectors():
+    """Regression vectors of oracle variant 1 (scripts/make_golden_python_variant.py; unpinned, see its header)."""
+    paths = sorted(glob.glob(os.path.join(GOLD, "pyvariant_*.npz")))
+    assert len(paths) >= 2
+    for path in paths:
+        g = np.load(path)
+        h, w, oh, ow, k = [int(v) for v in g["geom"]]
+        o = Oracle(h, w, oh, ow, k, variant=1).run(g["conf"], g["paf"])
+        assert np.array_equal(o["peaks"].view(np.uint8), g["peaks"].view(np.uint8))
+        assert np.array_equal(o["humans"].view(np.uint8), g["humans"].view(np.uint8))
+        assert [o["n_incomplete"], o["n_merges"], o["flags"]] == g["counts"].tolist()
