@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""GPU fuzz: the CUDA path against the CPU oracle on random geometries (integer and non-integer scales), kernel sizes,
+both variants, crowd sizes, missing limbs, noise and quantised (tie-rich) maps, one- to five-frame batches, pinned and
+pageable buffers.  Every stage is compared (tests/helpers.check_frame).   python scripts/fuzz_gpu_vs_oracle.py [seconds] [seed]"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle.oracle import Oracle  # noqa: E402
+from openpose_plus_b200 import synth, _capi as capi  # noqa: E402
+from openpose_plus_b200.engine import Engine  # noqa: E402
+import helpers  # noqa: E402
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+t0, n_frames, n_cfg, bad = time.time(), 0, 0, []
+while time.time() - t0 < budget:
+    fh, fw = [(46, 54), (23, 27), (30, 40), (12, 14)][int(rng.integers(4))]
+    kind = int(rng.integers(6))
+    scale = [8, 8, 8, 4, 2, 1][int(rng.integers(6))]
+    oh, ow = fh * scale, fw * scale
+    if kind == 5:
+        oh, ow = int(fh * rng.uniform(1.0, 6.0)), int(fw * rng.uniform(1.0, 6.0))
+    k = int(rng.choice([1, 3, 5, 7, 9, 13, 17, 25, 31]))
+    if k <= 7 and (scale > 2 or kind in (3, 5)):
+        continue
+    if k // 2 >= min(oh, ow) - 1:
+        continue
+    variant = int(rng.integers(4) == 0)
+    nb = int(rng.integers(1, 6))
+    frames = []
+    for _ in range(nb):
+        seed = int(rng.integers(1 << 30))
+        if kind in (0, 1, 5):
+            c, p = synth.render_frame(seed, int(rng.integers(1, 12)), fh, fw, noise=1e-3 if kind == 1 else 0.0)
+        elif kind == 2:
+            drop = tuple(int(x) for x in rng.choice(19, size=int(rng.integers(0, 4)), replace=False))
+            c, p = synth.render_frame(seed, int(rng.integers(15, 36)), fh, fw, drop_limbs=drop)
+        elif kind == 3:
+            c, p = synth.render_frame(seed, int(rng.integers(3, 10)), fh, fw, noise=0.02)
+        else:
+            c, p = synth.render_frame(seed, int(rng.integers(10, 30)), fh, fw)
+            c, p = (np.round(c * 8) / 8).astype(np.float32), (np.round(p * 4) / 4).astype(np.float32)
+        frames.append((c, p))
+    conf, paf = np.stack([f[0] for f in frames]), np.stack([f[1] for f in frames])
+    if rng.integers(2):
+        hc, hp = capi.pinned_empty(conf.shape, np.float32), capi.pinned_empty(paf.shape, np.float32)
+        hc[...], hp[...] = conf, paf
+    else:
+        hc, hp = conf, paf
+    eng = Engine(fh, fw, oh, ow, k, max_batch=5, max_peaks_per_part=512, max_cands_per_limb=8192, max_humans=512, variant=variant)
+    orc = Oracle(fh, fw, oh, ow, k, variant=variant)
+    try:
+        helpers.run_and_check(eng, orc, hc, hp, "fuzz %s" % ((fh, fw, oh, ow, k, variant, kind, nb),))
+    except AssertionError as e:
+        bad.append(str(e))
+        print("MISMATCH", e, flush=True)
+    eng.close()
+    n_frames += nb
+    n_cfg += 1
+print("configurations %d, frames %d, mismatches %d" % (n_cfg, n_frames, len(bad)))
+sys.exit(1 if bad else 0)
