@@ -276,3 +276,27 @@ def test_engine_takes_buffer_addresses_without_ndarray_ctypes():
     assert _ptr(rec[1:]) == rec[1:].ctypes.data and _ptr(None) is None
     with pytest.raises(TypeError):
         _ptr([1, 2, 3])
+
+
+def test_create_rejects_bad_configurations_before_touching_the_device():
+    """Argument errors are OPP_ERR_INVALID with a message, on any machine (the reference only asserts, src/post-process.h:37)."""
+    L = capi.lib()
+
+    def create(**kw):
+        cfg = capi.Config()
+        L.opp_config_default(C.byref(cfg), 46, 54, 368, 432, 17)
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        h = C.c_void_p()
+        rc = L.opp_create(C.byref(cfg), C.byref(h))
+        if rc == capi.OK:
+            L.opp_destroy(h)
+        return rc, (L.opp_last_error(None) or b"").decode()
+
+    for bad in (dict(n_joins=18), dict(n_connections=17), dict(gauss_kernel_size=16), dict(gauss_kernel_size=65), dict(gauss_kernel_size=0),
+                dict(out_h=40), dict(feat_h=1), dict(out_w=40000), dict(variant=7), dict(max_peaks_per_part=100000), dict(max_humans=100000)):
+        rc, msg = create(**bad)
+        assert rc == capi.ERR_INVALID and msg.startswith("opp_create:"), (bad, rc, msg)
+    rc, msg = create()
+    assert rc == (capi.OK if conftest.HAS_GPU else capi.ERR_NO_DEVICE), (rc, msg)
+    assert L.opp_bench_latency(None, None, 1, None) == capi.ERR_INVALID
