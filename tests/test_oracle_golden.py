@@ -152,3 +152,21 @@ def test_python_variant_oracle_reproduces_its_vectors():
         assert np.array_equal(o["peaks"].view(np.uint8), g["peaks"].view(np.uint8))
         assert np.array_equal(o["humans"].view(np.uint8), g["humans"].view(np.uint8))
         assert [o["n_incomplete"], o["n_merges"], o["flags"]] == g["counts"].tolist()
+
+
+def test_block_skipping_bound_holds_for_every_kernel_size():
+    """The peak kernels skip a block when every feature value its pixels depend on is <= t = 0.05f * (1 - 2^-13)
+    (DESIGN.md section 4, K2 step 2).  Every operation of the filter is monotone in its inputs (positive taps, IEEE
+    round-to-nearest), so the largest smoothed value such a block can reach is the one of the constant image t - which
+    must not exceed THRESH_HEAT.  Checked here in the filter's own float32 arithmetic for every kernel size and both
+    border rules."""
+    thr = np.float32(0.05)
+    t = np.float32(thr * np.float32(1.0 - 1.0 / 8192.0))
+    img = np.full((80, 80), t, np.float32)
+    for k in range(1, 64, 2):
+        s = Oracle.gauss_blur(img, k)
+        assert not (s > thr).any(), k
+        z = Oracle.smooth_zero_pad(img, Oracle.cdf_kernel(k))
+        assert not (z > thr).any(), k
+    # and the bound is not vacuous: a constant image just above the threshold does produce values above it
+    assert (Oracle.gauss_blur(np.full((80, 80), np.float32(0.0501), np.float32), 17) > thr).all()
