@@ -170,3 +170,27 @@ def test_block_skipping_bound_holds_for_every_kernel_size():
         assert not (z > thr).any(), k
     # and the bound is not vacuous: a constant image just above the threshold does produce values above it
     assert (Oracle.gauss_blur(np.full((80, 80), np.float32(0.0501), np.float32), 17) > thr).all()
+
+
+def test_fp32_forms_used_by_the_limb_kernel_equal_the_references_double_forms():
+    """csrc/opp_kernels.cu scores limbs without FP64 where an exact FP32 form exists; the three identities it relies on,
+    checked on the CPU in IEEE arithmetic:
+      (a) (float)sqrt((double)l2) == sqrtf((float)l2) for integer l2 < 2^24             (src/paf.cpp:91)
+      (b) (int)((double)v + 0.5) == t + (v - t >= 0.5f), t = (int)v, for 0 <= v < 2^23  (roundpaf, src/paf.cpp:337)
+      (c) min(0.0, 0.5 * H / (double)norm - 1.0) == 0 whenever norm <= 0.5f * H        (src/paf.cpp:115-116)"""
+    d = np.arange(0, 2049, dtype=np.int64)
+    l2 = (d[:, None] ** 2 + d[None, :] ** 2).ravel()
+    l2 = np.unique(l2[l2 < (1 << 24)])
+    assert np.array_equal(np.sqrt(l2.astype(np.float64)).astype(np.float32), np.sqrt(l2.astype(np.float32)))
+    rng = np.random.default_rng(0)
+    v = np.concatenate([rng.uniform(0, 4096, 2_000_000), np.arange(0, 4096, 0.5), np.nextafter(np.arange(0.5, 4096, 1.0), 0),
+                        np.nextafter(np.arange(0.5, 4096, 1.0), 1e9)]).astype(np.float32)
+    want = (v.astype(np.float64) + 0.5).astype(np.int64)
+    t = v.astype(np.int32)
+    got = t + ((v - t.astype(np.float32)) >= np.float32(0.5))
+    assert np.array_equal(got, want)
+    for H in (368, 736, 300, 97):
+        norm = np.sqrt(l2[(l2 > 0) & (l2 < 4 * H * H)].astype(np.float32))
+        inside = norm <= np.float32(0.5) * np.float32(H)
+        pen = np.minimum(0.0, 0.5 * H / norm[inside].astype(np.float64) - 1.0)
+        assert (pen == 0.0).all()
