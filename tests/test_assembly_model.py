@@ -90,7 +90,8 @@ def virtual_limb(mem, conns_l, l, ps, state):
             if len(hs) == 1 and live[hs[0]]["parts"][p2] == -1:
                 extend(live[hs[0]], c)
     for c in conns_l[k0:]:  # src/paf.cpp:192-248 for a virtual pair
-        ids = [h["id"] for h in mem[:state["n"]] if h["parts"][p1] == c["cid1"] or h["parts"][p2] == c["cid2"]]
+        # src/paf.cpp:198 collects the STORED ids (stale after an erase); the Python path's pafprocess the positions
+        ids = [(q if state["true_index"] else h["id"]) for q, h in enumerate(mem[:state["n"]]) if h["parts"][p1] == c["cid1"] or h["parts"][p2] == c["cid2"]]
         if len(ids) == 1:
             if ids[0] >= state["hist_max"]:
                 state["ub"] = True
@@ -119,12 +120,12 @@ def virtual_limb(mem, conns_l, l, ps, state):
                 state["merges"] += 1
 
 
-def model(o):
+def model(o, true_index=False):
     peaks = o["peaks"]
     ps = lambda i: f32(peaks["score"][i])  # noqa: E731
     pofs = np.concatenate([[0], np.cumsum([(peaks["part_id"] == k).sum() for k in range(18)])])
     mem = forest(o["conns"], ps, pofs)
-    state = dict(merges=0, n=len(mem), hist_max=len(mem), ub=False)
+    state = dict(merges=0, n=len(mem), hist_max=len(mem), ub=False, true_index=true_index)
     for l in (17, 18):
         virtual_limb(mem, list(o["conns"][l]), l, ps, state)
     return mem[:state["n"]], state
@@ -156,3 +157,22 @@ def test_forest_and_virtual_prefix_model_reproduces_the_oracle():
         checked += 1
         merged += st["merges"]
     assert checked >= 25 and merged >= 20
+
+
+def test_position_indexed_model_reproduces_oracle_variant_1():
+    """The same decomposition with humans indexed by position (OPP_VARIANT_PYTHON, the pafprocess rule): an independent
+    statement of the grouping half of oracle variant 1.  Positions are never stale, so no frame is skipped."""
+    orc = Oracle(46, 54, 368, 432, 25, variant=1)
+    merged = 0
+    for n_frames, (conf, paf) in enumerate(frames()):
+        o = orc.run(conf, paf, lazy=True)
+        humans, st = model(o, true_index=True)
+        assert not st["ub"] and o["flags"] == 0
+        assert len(humans) == o["n_incomplete"] and st["merges"] == o["n_merges"]
+        keep = [h for h in humans if not (h["n"] < 4 or f32(h["score"] / f32(h["n"])) < f32(0.4))]
+        assert len(keep) == o["n_humans"]
+        for h, r in zip(keep, o["hrefs"]):
+            assert h["parts"] == r["parts"].tolist() and h["n"] == r["n_parts"]
+            assert np.float32(h["score"]).view(np.uint32) == np.float32(r["score"]).view(np.uint32)
+        merged += st["merges"]
+    assert n_frames >= 39 and merged >= 50
