@@ -82,3 +82,86 @@ def test_feature_level_arithmetic_equals_blurring_the_replicated_image(S, ksizes
             want = Oracle.gauss_blur(img, ksize)
             got = fast_model(F, S, ksize)
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (S, ksize, h, w)
+
+
+def reflect101(p, n):
+    if p < 0:
+        return -p
+    if p >= n:
+        return 2 * (n - 1) - p
+    return p
+
+
+def generic_rep_model(F, S, ksize, zero, taps, GTX=64, GTY=32):
+    """k2_peaks_generic_rep, tile by tile, with the kernel's own index formulas (f_lo, nfr, row map with an all-zero
+    row, column expansion rx / S): returns the smoothed image."""
+    h, w = F.shape
+    H, W, R = S * h, S * w, ksize // 2
+    IW, IH, TW = GTX + 2 + 2 * R, GTY + 2 + 2 * R, GTX + 2
+    out = np.full((H, W), np.nan, np.float32)
+    clip = lambda v, n: min(max(v, 0), n - 1)  # noqa: E731
+    for y0 in range(0, H, GTY):
+        for x0 in range(0, W, GTX):
+            ylo, yhi = max(y0 - 1 - R, 0), min(y0 + GTY + R, H - 1)
+            f_lo = ylo // S
+            nfr = yhi // S - f_lo + 1
+            rowmap = []
+            for i in range(IH):
+                yy = y0 - 1 - R + i
+                if zero:
+                    m = nfr if (yy < 0 or yy >= H) else yy // S - f_lo
+                else:
+                    m = min(max(clip(reflect101(yy, H), H) // S - f_lo, 0), nfr - 1)
+                rowmap.append(m)
+            inn = np.zeros((nfr, IW), np.float32)
+            for fr in range(nfr):
+                for t in range(IW):
+                    xx = x0 - 1 - R + t
+                    inn[fr, t] = f32(0) if (zero and (xx < 0 or xx >= W)) else F[f_lo + fr, clip(reflect101(xx, W), W) // S]
+            tmp = np.zeros((nfr + 1, TW), np.float32)
+            for fr in range(nfr):
+                for c in range(TW):
+                    q = inn[fr, c:c + ksize]
+                    if ksize == 3 and not zero:
+                        s = f32(f32(q[R] * taps[R]) + f32(f32(q[R - 1] + q[R + 1]) * taps[R + 1]))
+                    elif ksize == 5 and not zero:
+                        s = f32(f32(q[R] * taps[R]) + f32(f32(q[R - 1] + q[R + 1]) * taps[R + 1]))
+                        s = f32(s + f32(f32(q[R - 2] + q[R + 2]) * taps[R + 2]))
+                    else:
+                        s = f32(taps[0] * q[0])
+                        for j in range(1, ksize):
+                            s = f32(s + f32(taps[j] * q[j]))
+                    tmp[fr, c] = s
+            for r in range(1, GTY + 1):
+                y = y0 - 1 + r
+                if y >= H:
+                    break
+                for c in range(1, TW - 1):
+                    x = x0 - 1 + c
+                    if x >= W:
+                        break
+                    rm = lambda j: rowmap[r + R + j]  # noqa: E731
+                    s = f32(taps[R] * tmp[rm(0), c])
+                    for j in range(1, R + 1):
+                        s = f32(s + f32(taps[R + j] * f32(tmp[rm(j), c] + tmp[rm(-j), c])))
+                    out[y, x] = s
+    return out
+
+
+@pytest.mark.parametrize("zero", [False, True])
+def test_replication_aware_generic_kernel_model(zero):
+    """The row map of k2_peaks_generic_rep (image row -> feature row of the row-pass result, REFLECT_101 or an all-zero row
+    for tf 'SAME' padding) gives the same smoothed image as filtering the materialised map, bit for bit."""
+    rng = np.random.default_rng(5)
+    for (S, ksize, h, w) in ((8, 25, 5, 9), (8, 19, 9, 3), (4, 13, 11, 17), (2, 9, 20, 37), (1, 7, 40, 70), (8, 3, 5, 9), (4, 5, 9, 17)):
+        F = rng.random((h, w), dtype=np.float32)
+        img = np.repeat(np.repeat(F, S, 0), S, 1)
+        if zero:
+            taps = Oracle.cdf_kernel(ksize)
+            want = Oracle.smooth_zero_pad(img, taps)
+        else:
+            taps = Oracle.gauss_kernel(ksize)
+            want = Oracle.gauss_blur(img, ksize)
+        got = generic_rep_model(F, S, ksize, zero, taps)
+        assert not np.isnan(got).any()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (S, ksize, h, w, zero)
