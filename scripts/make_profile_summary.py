@@ -79,7 +79,9 @@ out.append("Earlier captures of this round are kept for the optimisation history
            "lane, 86.5 k frames/s materialised / 156 k skeleton-only) and `r1_v2_k2_ncu_raw.csv` (two columns per lane, shared tap products).\n")
 out.append("SASS evidence (`cuobjdump -sass openpose_plus_b200/libopp_b200.so`): `UBLKCP.S.G` + `SYNCS.ARRIVE.TRANS64` / `SYNCS.PHASECHK.TRANS64.TRYWAIT` "
            "(TMA bulk load of the PAF tile in `k3_limbs`, mbarrier completion), `UBLKCP.G.S` (TMA bulk-store resize variant), `LDGSTS` (cp.async tile "
-           "staging in `k2_peaks_fast`), `STG.E.EF.128` (streaming 16-byte stores of the up-sampled maps). No tensor-core instructions: no stage is a contraction.\n")
+           "staging in `k2_peaks_fast`), `STG.E.EF.128` (streaming 16-byte stores of the up-sampled maps), `ACQBULK` / `PREEXIT` (`griddepcontrol.wait` / `.launch_dependents` of the "
+           "programmatic dependent launches on the latency path), `MEMBAR.SC.SYS` (system-scope fence ahead of the pinned completion word). "
+           "No tensor-core instructions: no stage is a contraction.\n")
 out.append("compute-sanitizer is closed on this pool (the tool answers so); memory safety is covered by capacity checks in the kernels, the overflow "
            "flags and the stage-by-stage comparison with the CPU oracle in the GPU tests (`pytest -m gpu`).\n")
 open(os.path.join(P, "README.md"), "w").write("\n".join(out))
