@@ -2,12 +2,28 @@
 // include/openpose-plus.hpp:42-64 for the post-processing path: callers keep
 //     std::unique_ptr<paf_processor> p(create_paf_processor(fh, fw, H, W, 19, 19, ksize));
 //     std::vector<human_t> humans = (*p)(heatmap, paf, use_gpu);
-// The CNN runner (pose_detection_runner, TensorRT) is out of scope of this build and not declared.
+// The CNN runner (pose_detection_runner, TensorRT; reference include/openpose-plus.hpp:9-36) is out of scope of this
+// build: it is DECLARED below, unchanged, so that translation units of the reference that implement or call it
+// (src/uff-runner.cpp, examples/*.cpp) keep compiling against this header; libopp_b200.so does not define it.
 #pragma once
 #include <string>
 #include <vector>
 
 #include <openpose-plus/human.h>
+
+// Feature-map producer: image batch in, heat maps [batch, 19, H', W'] and PAFs [batch, 38, H', W'] out.
+class pose_detection_runner
+{
+  public:
+    // inputs: one pointer to float[max_batch_size * 3 * H * W]; outputs: two pointers (heat maps, PAFs)
+    virtual void operator()(const std::vector<void *> &inputs, const std::vector<void *> &outputs, int batchSize = 1) = 0;
+
+    virtual ~pose_detection_runner() {}
+};
+
+// Defined by the reference's TensorRT runner (src/uff-runner.cpp), not by this library.
+pose_detection_runner *create_pose_detection_runner(const std::string &model_file, int input_height, int input_width,
+                                                    int max_batch_size, bool use_f16);
 
 class paf_processor
 {

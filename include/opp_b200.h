@@ -59,6 +59,16 @@ enum { OPP_VARIANT_CPP = 0, OPP_VARIANT_PYTHON = 1 };
 
 enum { OPP_MEM_HOST = 0, OPP_MEM_DEVICE = 1 };
 enum { OPP_LAYOUT_CHW = 0, OPP_LAYOUT_HWC = 1 };
+/* How DEVICE-resident inputs of a batch become ready (opp_batch_t.in_sync).  The feature maps normally come from a
+ * CNN runner working on its own stream (src/uff-runner.cpp:199-205 executes the TensorRT context, then copies the maps
+ * to the host only because paf_processor wants host pointers): with STREAM / EVENT the hand-off is ordered on the
+ * device and the caller never synchronises the host. */
+enum {
+    OPP_SYNC_NONE = 0,   /* the inputs are complete when opp_submit is called (host memory, or the caller synchronised) */
+    OPP_SYNC_STREAM = 1, /* in_sync_obj is the producer's cudaStream_t (NULL = the legacy default stream): the batch
+                          * waits for everything enqueued on it so far (the library records its own event there) */
+    OPP_SYNC_EVENT = 2   /* in_sync_obj is a cudaEvent_t the caller has recorded after the producer's last write */
+};
 
 /* include/openpose-plus/human.h:8-15 (bool + 3 pad bytes, then 3 floats) */
 typedef struct {
@@ -124,10 +134,18 @@ typedef struct {
     float *conf_up;        /* [n, 19, H, W] (CHW) or [n, H, W, 19] (up_layout HWC) */
     float *paf_up;         /* [n, 38, H, W] (CHW) or [n, H, W, 38] */
     int32_t up_layout;
-    int32_t reserved[3];
+    int32_t in_sync;       /* OPP_SYNC_*: ordering of device-resident conf / paf (and of conf_up / paf_up re-use) against
+                            * the producer; ignored for host inputs */
+    void *in_sync_obj;     /* cudaStream_t or cudaEvent_t, see OPP_SYNC_* */
 } opp_batch_t;
 
 typedef struct opp_handle_s *opp_handle_t;
+
+/* Threading contract: a handle is used by ONE host thread at a time (like the reference's paf_processor instance,
+ * whose scratch members make it non-reentrant: src/paf.cpp:74-77, examples/stream_detector.cpp:120-136); different
+ * handles - on the same or on different GPUs - may be driven from different threads concurrently.  opp_host_alloc /
+ * opp_host_free / opp_host_register / opp_host_unregister are thread-safe.  Every entry point leaves the caller's
+ * current CUDA device unchanged. */
 
 void opp_config_default(opp_config_t *cfg, int feat_h, int feat_w, int out_h, int out_w, int gauss_kernel_size);
 
@@ -153,6 +171,20 @@ int64_t opp_launch_count(opp_handle_t h);
 /* Pinned host memory for opp_batch_t host buffers (pageable memory also works, slower). */
 void *opp_host_alloc(size_t bytes);
 void opp_host_free(void *p);
+/* Flags for opp_host_alloc_ex.  WRITE_COMBINED memory is for INPUT buffers a producer only writes (the GPU reads it
+ * over PCIe without snooping the CPU caches; CPU reads of it are very slow): never use it for result buffers. */
+enum { OPP_HOST_DEFAULT = 0, OPP_HOST_WRITE_COMBINED = 1 };
+void *opp_host_alloc_ex(size_t bytes, int flags);
+/* Pins memory the caller already owns (e.g. a shared-memory segment several processes map, so that the ranks of a
+ * multi-GPU job write their skeletons straight into one host buffer: the "host gather" of BASELINE.json configs[4]
+ * without a copy).  p and bytes should be page-aligned.  Returns OPP_OK or OPP_ERR_CUDA. */
+int opp_host_register(void *p, size_t bytes);
+int opp_host_unregister(void *p);
+
+/* Makes `stream` (a cudaStream_t of the caller) wait for the batch behind `ticket` without blocking the host:
+ * the device-side counterpart of opp_wait for consumers of device-resident results (out_mem = OPP_MEM_DEVICE,
+ * conf_up / paf_up).  The slot stays in flight until opp_wait(ticket) is called. */
+int opp_stream_wait_ticket(opp_handle_t h, int ticket, void *stream);
 
 /* Intermediates of the last batch processed on `ticket`'s slot, for parity tests.  Each call copies
  * up to cap elements of frame `frame` to host memory and returns the element count (<0 on error).

@@ -17,6 +17,8 @@ FLAG_UB_STALE_INDEX, FLAG_UB_PEAK_INDEX, FLAG_UB_ERASE_PAST_END = 8, 16, 32
 FLAG_OVERFLOW_MASK = 7
 VARIANT_CPP, VARIANT_PYTHON = 0, 1
 DBG_PEAKS, DBG_CONNS, DBG_PARTS, DBG_COUNTS = 0, 1, 2, 3
+SYNC_NONE, SYNC_STREAM, SYNC_EVENT = 0, 1, 2
+HOST_DEFAULT, HOST_WRITE_COMBINED = 0, 1
 
 PART_DT = np.dtype([("has_value", "u1"), ("pad", "u1", (3,)), ("x", "<f4"), ("y", "<f4"), ("score", "<f4")])
 HUMAN_DT = np.dtype([("parts", PART_DT, (N_PARTS,)), ("score", "<f4")])
@@ -35,7 +37,10 @@ class Batch(C.Structure):
     _fields_ = [("conf", C.c_void_p), ("paf", C.c_void_p), ("n_frames", C.c_int32), ("in_mem", C.c_int32),
                 ("in_layout", C.c_int32), ("out_mem", C.c_int32), ("humans", C.c_void_p), ("n_humans", C.c_void_p),
                 ("frame_flags", C.c_void_p), ("conf_up", C.c_void_p), ("paf_up", C.c_void_p), ("up_layout", C.c_int32),
-                ("reserved", C.c_int32 * 3)]
+                ("in_sync", C.c_int32), ("in_sync_obj", C.c_void_p)]
+
+
+assert C.sizeof(Batch) == 88 and C.sizeof(Config) == 64  # static_assert'ed on the C side too
 
 
 class OppError(RuntimeError):
@@ -72,6 +77,11 @@ def lib():
         L.opp_host_alloc.restype = C.c_void_p
         L.opp_host_free.argtypes = [C.c_void_p]
         L.opp_host_free.restype = None
+        L.opp_host_alloc_ex.argtypes = [C.c_size_t, C.c_int]
+        L.opp_host_alloc_ex.restype = C.c_void_p
+        L.opp_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        L.opp_host_unregister.argtypes = [C.c_void_p]
+        L.opp_stream_wait_ticket.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.opp_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.opp_resize_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.opp_resize_pair_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -89,18 +99,20 @@ def lib():
 
 
 EXPORTS = ["opp_config_default", "opp_create", "opp_destroy", "opp_process", "opp_submit", "opp_wait",
-           "opp_last_batch_ms", "opp_launch_count", "opp_device", "opp_host_alloc", "opp_host_free", "opp_debug_fetch",
+           "opp_last_batch_ms", "opp_launch_count", "opp_device", "opp_host_alloc", "opp_host_free", "opp_host_alloc_ex",
+           "opp_host_register", "opp_host_unregister", "opp_stream_wait_ticket", "opp_debug_fetch",
            "opp_resize_device", "opp_resize_pair_device", "opp_peaks_device", "opp_timer_start", "opp_timer_stop", "opp_last_error", "opp_version", "opp_draw_human", "opp_bench_latency", "process_conf_paf"]
 
 
-def pinned_empty(shape, dtype):
-    """numpy array over cudaMallocHost memory; freed when the last view of it is collected."""
+def pinned_empty(shape, dtype, write_combined=False):
+    """numpy array over pinned host memory; freed when the last view of it is collected.  write_combined=True is for
+    INPUT buffers the host only writes (see OPP_HOST_WRITE_COMBINED)."""
     import weakref
     dtype = np.dtype(dtype)
     count = int(np.prod(shape))
     n = max(count * dtype.itemsize, 1)
     L = lib()
-    p = L.opp_host_alloc(n)
+    p = L.opp_host_alloc_ex(n, HOST_WRITE_COMBINED if write_combined else HOST_DEFAULT)
     if not p:
         raise MemoryError("opp_host_alloc(%d) failed" % n)
     buf = (C.c_char * n).from_address(p)

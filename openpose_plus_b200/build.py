@@ -36,5 +36,28 @@ def build(force=False, verbose=False):
     return OUT
 
 
+REF_INCLUDE = "/root/reference/include"
+DROPIN_REF = os.path.join(ROOT, "tests", "cpp", "_build", "dropin_refhdr")
+
+
+def build_dropin_against_reference_headers(force=False):
+    """tests/cpp/dropin_main.cpp - a caller written against the reference's public API only - compiled against the
+    reference's OWN, unmodified headers (not this repo's re-written ones) and linked with libopp_b200.so: pins the ABI
+    claim (vtable order of paf_processor, human_t layout, factory signature).  The reference tree exists only in the
+    build container; the binary (git-ignored) travels to the GPU box, where the -m gpu tests run it.  Returns the path,
+    or None when the reference headers are absent and no prebuilt binary exists."""
+    src = os.path.join(ROOT, "tests", "cpp", "dropin_main.cpp")
+    if not os.path.exists(os.path.join(REF_INCLUDE, "openpose-plus.hpp")):
+        return DROPIN_REF if os.path.exists(DROPIN_REF) else None
+    if not force and os.path.exists(DROPIN_REF) and os.path.getmtime(DROPIN_REF) >= max(os.path.getmtime(src), os.path.getmtime(OUT)):
+        return DROPIN_REF
+    os.makedirs(os.path.dirname(DROPIN_REF), exist_ok=True)
+    # `-include string`: the reference's openpose-plus.hpp uses std::string without including it (SURVEY 8b)
+    cmd = ["g++", "-std=c++14", "-O1", "-include", "string", "-I", REF_INCLUDE, src, "-o", DROPIN_REF, "-L", HERE, "-l:libopp_b200.so",
+           "-Wl,-rpath,$ORIGIN/../../../openpose_plus_b200", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    subprocess.run(cmd, check=True)
+    return DROPIN_REF
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

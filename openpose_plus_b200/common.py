@@ -32,6 +32,21 @@ CocoPairs = [(1, 2), (1, 5), (2, 3), (3, 4), (5, 6), (6, 7), (1, 8), (8, 9), (9,
 CocoPairsRender = CocoPairs[:-2]
 
 
+def tranform_keypoints2d(body, width, height, kp_score_thresh=0.25):
+    """(sic) The reference's helper of that name (openpose_plus/inference/common.py:86-96): `body` is a
+    Human.body_parts dict {part_idx: BodyPart}; returns (coords2d [18,2] float64 in pixels, coords2d_conf [18] float64,
+    coords2d_vis [18] bool = score > kp_score_thresh)."""
+    coords2d = np.zeros((18, 2))
+    coords2d_conf = np.zeros((18))
+    coords2d_vis = coords2d_conf > 0.0
+    for i, part in body.items():
+        coords2d_conf[i] = part.score
+        coords2d[i, 0] = part.x * width
+        coords2d[i, 1] = part.y * height
+        coords2d_vis[i] = coords2d_conf[i] > kp_score_thresh
+    return coords2d, coords2d_conf, coords2d_vis
+
+
 def keypoints_array(human, image_w, image_h):
     """[18, 3] array of (x px, y px, score), zeros where a part is missing."""
     out = np.zeros((18, 3), np.float32)

@@ -14,6 +14,8 @@
 
 #include "opp_kernels.cuh"
 
+static_assert(sizeof(opp_batch_t) == 88 && sizeof(opp_config_t) == 64, "C-ABI struct layout is part of the contract (ctypes mirrors it)");
+
 namespace
 {
 thread_local std::string g_err;
@@ -33,6 +35,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr; // materialising resize runs beside peak finding / grouping
     cudaEvent_t ev_start = nullptr, ev_done = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_in = nullptr; // recorded on the producer's stream (OPP_SYNC_STREAM)
     cudaEvent_t tr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // OPP_TRACE: k1 start/end, k2 start/end, k3 end, copies end
     // device arena
     float *d_conf = nullptr, *d_paf = nullptr; // staged feature maps [B,19,h,w] / [B,38,h,w]
@@ -185,6 +188,15 @@ int area_coeffs(int ssize, int dsize, bool clamp_edge, std::vector<int> &ofs, st
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#elif defined(__aarch64__)
+    asm volatile("yield" ::: "memory");
+#endif
+}
+
 void plan_k3_smem(opp_handle_s *h)
 {
     K3Params &p = h->k3_plan;
@@ -237,6 +249,7 @@ int free_slot(opp_handle_s *h, Slot &s)
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     if (s.ev_join) cudaEventDestroy(s.ev_join);
+    if (s.ev_in) cudaEventDestroy(s.ev_in);
     if (s.side) cudaStreamDestroy(s.side);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
@@ -260,6 +273,7 @@ int alloc_slot(opp_handle_s *h, Slot &s)
     CU(cudaEventCreate(&s.ev_done));
     CU(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
     if (h->trace) {
         for (auto &e : s.tr) CU(cudaEventCreate(&e));
         CU(cudaMalloc(&s.d_times, (B * OPP_N_PAIRS * 12 + 4096 * 8) * sizeof(unsigned long long)));
@@ -321,22 +335,25 @@ void *mapped_host(const void *p)
     return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
-void choose_k2_tiles(opp_handle_s *h, int n_frames, bool store, int &tw, int &th)
+// Tile plan of the integer-scale peak kernel.  Limits of the kernel itself (k2_peaks_fast / launch_k2_fast_t): a column
+// strip holds at most 62 feature columns (+2 halo columns in the 64-bit activity masks) and at most 7 warps x 62 decided
+// image columns; a row tile at most 60 feature rows (+4 halo rows).  Returns false when no valid plan exists for this
+// geometry (opp_create then selects the replication-aware generic kernel instead of failing at launch time).
+bool choose_k2_tiles(opp_handle_s *h, int n_frames, bool store, int &tw, int &th)
 {
     const OppGeom &g = h->g;
-    // column strips of at most 7 warps x 62 decided columns (K2_FAST_MAX_THREADS = 224)
     const int S = g.S > 0 ? g.S : 1;
-    int nxs = (g.W + 62 * 7 - 1) / (62 * 7);
-    if (nxs < 1) nxs = 1;
+    int tw_max = (62 * K2_FAST_MAX_GROUPS) / S;
+    if (tw_max > 62) tw_max = 62;
+    if (tw_max < 1) return false;
+    const int nxs = (g.w + tw_max - 1) / tw_max;
     tw = (g.w + nxs - 1) / nxs;
-    th = g.h;
-    (void)S;
     // three resident CTAs per SM (the kernel is compiled for that): each must stay under ~72 KB, and
     // row tiles of about 16 feature rows keep the last wave short
     // (measured at 368x432: ~8 rows when the kernel also streams the up-sampled maps - short tiles
     // keep the store flow even - and ~23 rows in skeleton-only mode, where per-CTA fixed costs dominate)
     const int target = store ? 8 : 23;
-    int nys = (g.h + target - 1) / target;
+    const int nys = (g.h + target - 1) / target;
     th = (g.h + nys - 1) / nys;
     while ((k2_fast_smem_bytes(g, tw, th) > (size_t)72 * 1024 || th > 60) && th > 4) th = (th + 1) / 2;
     // small batches: split rows too until the grid covers the chip about twice
@@ -344,6 +361,9 @@ void choose_k2_tiles(opp_handle_s *h, int n_frames, bool store, int &tw, int &th
     while ((long)n_frames * OPP_N_PARTS * ((g.w + tw - 1) / tw) * ((g.h + th - 1) / th) < want && th > 6) th = (th + 1) / 2;
     if (h->force_tw > 0) tw = h->force_tw;
     if (h->force_th > 0) th = h->force_th;
+    const int groups = (S * tw + 61) / 62;
+    return tw >= 1 && th >= 1 && tw + 2 <= 64 && th + 4 <= 64 && groups >= 1 && groups <= K2_FAST_MAX_GROUPS &&
+           k2_fast_smem_bytes(g, tw, th) <= (size_t)h->max_smem - 1024;
 }
 
 } // namespace
@@ -368,13 +388,8 @@ void opp_config_default(opp_config_t *cfg, int feat_h, int feat_w, int out_h, in
     cfg->n_slots = 3;
 }
 
-void *opp_host_alloc(size_t bytes)
+static void remember_pinned(void *p, size_t bytes)
 {
-    void *p = nullptr;
-    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
-        set_err(nullptr, "cudaMallocHost(%zu) failed", bytes);
-        return nullptr;
-    }
     void *d = nullptr;
     if (cudaHostGetDevicePointer(&d, p, 0) == cudaSuccess && d) {
         std::lock_guard<std::mutex> lk(g_pin_mu);
@@ -382,20 +397,63 @@ void *opp_host_alloc(size_t bytes)
     } else {
         cudaGetLastError();
     }
+}
+
+static void forget_pinned(void *p)
+{
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (size_t i = 0; i < g_pins.size(); ++i)
+        if (g_pins[i].base == reinterpret_cast<uintptr_t>(p)) {
+            g_pins.erase(g_pins.begin() + i);
+            break;
+        }
+}
+
+void *opp_host_alloc_ex(size_t bytes, int flags)
+{
+    void *p = nullptr;
+    // portable: usable from every device of the process (one handle per GPU, process_stream_multi)
+    unsigned f = cudaHostAllocPortable | cudaHostAllocMapped;
+    if (flags & OPP_HOST_WRITE_COMBINED) f |= cudaHostAllocWriteCombined;
+    if (cudaHostAlloc(&p, bytes, f) != cudaSuccess) {
+        set_err(nullptr, "cudaHostAlloc(%zu, %u) failed", bytes, f);
+        cudaGetLastError();
+        return nullptr;
+    }
+    remember_pinned(p, bytes);
     return p;
+}
+
+void *opp_host_alloc(size_t bytes) { return opp_host_alloc_ex(bytes, OPP_HOST_DEFAULT); }
+
+int opp_host_register(void *p, size_t bytes)
+{
+    if (!p || !bytes) return OPP_ERR_INVALID;
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) {
+        set_err(nullptr, "cudaHostRegister(%p, %zu) failed: %s", p, bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return OPP_ERR_CUDA;
+    }
+    remember_pinned(p, bytes);
+    return OPP_OK;
+}
+
+int opp_host_unregister(void *p)
+{
+    if (!p) return OPP_ERR_INVALID;
+    forget_pinned(p);
+    if (cudaHostUnregister(p) != cudaSuccess) {
+        cudaGetLastError();
+        return OPP_ERR_CUDA;
+    }
+    return OPP_OK;
 }
 
 void opp_host_free(void *p)
 {
     if (!p) return;
-    {
-        std::lock_guard<std::mutex> lk(g_pin_mu);
-        for (size_t i = 0; i < g_pins.size(); ++i)
-            if (g_pins[i].base == reinterpret_cast<uintptr_t>(p)) {
-                g_pins.erase(g_pins.begin() + i);
-                break;
-            }
-    }
+    forget_pinned(p);
     cudaFreeHost(p);
 }
 
@@ -500,6 +558,12 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
         }
         if (const char *e = getenv("OPP_K2_TW")) h->force_tw = atoi(e);
         if (const char *e = getenv("OPP_K2_TH")) h->force_th = atoi(e);
+        if (h->fast_k2) { // every batch size and both modes must have a launchable tile plan, else the generic kernel takes over
+            int tw_ = 0, th_ = 0;
+            for (int store = 0; store < 2 && h->fast_k2; ++store)
+                for (int nf = 1; nf <= c.max_batch && h->fast_k2; nf = nf < c.max_batch && 2 * nf > c.max_batch ? c.max_batch : 2 * nf)
+                    if (!choose_k2_tiles(h, nf, store != 0, tw_, th_)) h->fast_k2 = false;
+        }
         plan_k3_smem(h);
         if (h->k3_smem > (size_t)h->max_smem) {
             set_err(&h->err, "opp_create: capacities need %zu bytes of shared memory (> %d)", h->k3_smem, h->max_smem);
@@ -552,6 +616,14 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     const int n = b.n_frames;
     const size_t hw = (size_t)g.h * g.w, HW = (size_t)g.H * g.W;
     cudaStream_t st = s.stream;
+    // Device-resident maps written by a producer on its own stream (the CNN runner, src/uff-runner.cpp:199-205): the
+    // slot's stream waits for it on the device; the host is never synchronised.
+    if (b.in_sync == OPP_SYNC_STREAM) {
+        CU(cudaEventRecord(s.ev_in, (cudaStream_t)b.in_sync_obj));
+        CU(cudaStreamWaitEvent(st, s.ev_in, 0));
+    } else if (b.in_sync == OPP_SYNC_EVENT) {
+        CU(cudaStreamWaitEvent(st, (cudaEvent_t)b.in_sync_obj, 0));
+    }
     CU(cudaEventRecord(s.ev_start, st));
     // A few frames in host memory take the latency path.  Pinned buffers are read in place; PAGEABLE ones (what a
     // caller of the reference's paf_processor passes) are first copied by this thread into the slot's pinned staging:
@@ -683,7 +755,7 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     // ---- peaks
     if (h->trace) CU(cudaEventRecord(s.tr[2], st));
     K2Params k2{};
-    fill_k2(h, s, conf, conf_up_for_k2, n, fuse_up, k2);
+    if (int r = fill_k2(h, s, conf, conf_up_for_k2, n, fuse_up, k2)) return r;
     if (fuse_up) k2.paf = paf, k2.up_conf = b.conf_up, k2.up_paf = b.paf_up;
     if (s.d_times && n == 1) k2.times = s.d_times + (size_t)c.max_batch * OPP_N_PAIRS * 12;
     int *d_flags = cnt_flags(h, s);
@@ -777,13 +849,28 @@ int opp_submit(opp_handle_t h, const opp_batch_t *b, int *ticket)
         set_err(&h->err, "opp_submit: bad memory kind or layout");
         return OPP_ERR_INVALID;
     }
+    if (b->in_sync != OPP_SYNC_NONE && b->in_sync != OPP_SYNC_STREAM && b->in_sync != OPP_SYNC_EVENT) {
+        set_err(&h->err, "opp_submit: in_sync must be OPP_SYNC_NONE, OPP_SYNC_STREAM or OPP_SYNC_EVENT");
+        return OPP_ERR_INVALID;
+    }
+    if (b->in_sync == OPP_SYNC_EVENT && !b->in_sync_obj) {
+        set_err(&h->err, "opp_submit: OPP_SYNC_EVENT needs a cudaEvent_t in in_sync_obj");
+        return OPP_ERR_INVALID;
+    }
     DeviceGuard guard_(h->device);
-    const int si = h->next_slot;
-    Slot &s = h->slots[si];
-    if (s.busy) {
-        set_err(&h->err, "opp_submit: all %d slots in flight; call opp_wait first", (int)h->slots.size());
+    // first free slot at or after next_slot: tickets may be waited in any order
+    const int ns = (int)h->slots.size();
+    int si = -1;
+    for (int k = 0; k < ns; ++k)
+        if (!h->slots[(h->next_slot + k) % ns].busy) {
+            si = (h->next_slot + k) % ns;
+            break;
+        }
+    if (si < 0) {
+        set_err(&h->err, "opp_submit: all %d slots in flight; call opp_wait first", ns);
         return OPP_ERR_BUSY;
     }
+    Slot &s = h->slots[si];
     s.batch = *b, s.n_frames = b->n_frames;
     const int rc = enqueue(h, s, *b);
     if (rc != OPP_OK) {
@@ -820,9 +907,11 @@ int opp_wait(opp_handle_t h, int ticket)
     bool retired = true;
     if (s.done_tag) {
         // spin on the completion word; look at the event now and then so that a failed launch cannot hang the caller
-        volatile int *f = s.h_done;
+        // (acquire: the results in pinned memory are read after the word; on weakly ordered hosts - aarch64 - a plain
+        // load would let those reads be satisfied first)
         retired = false;
-        for (unsigned spins = 1; *f != s.done_tag; ++spins) {
+        for (unsigned spins = 1; __atomic_load_n(s.h_done, __ATOMIC_ACQUIRE) != s.done_tag; ++spins) {
+            cpu_relax();
             if ((spins & 0x3fff) == 0) {
                 const cudaError_t q = cudaEventQuery(s.ev_done);
                 if (q != cudaErrorNotReady) {
@@ -891,6 +980,19 @@ int opp_wait(opp_handle_t h, int ticket)
             if (nh > 0) std::memcpy(b.humans + (size_t)f * capH, s.h_humans + (size_t)f * capH, nh * sizeof(opp_human_t));
         }
     }
+    return OPP_OK;
+}
+
+int opp_stream_wait_ticket(opp_handle_t h, int ticket, void *stream)
+{
+    if (!h) return OPP_ERR_INVALID;
+    Slot *sp = slot_of(h, ticket);
+    if (!sp || !sp->busy) {
+        set_err(&h->err, "opp_stream_wait_ticket: unknown ticket %d", ticket);
+        return OPP_ERR_INVALID;
+    }
+    DeviceGuard guard_(h->device);
+    CU(cudaStreamWaitEvent((cudaStream_t)stream, sp->ev_done, 0));
     return OPP_OK;
 }
 
@@ -996,7 +1098,10 @@ static int fill_k2(opp_handle_s *h, Slot &s, const float *conf, const float *con
     k2.border_zero = c.variant == OPP_VARIANT_PYTHON;
     k2.skip_thresh = h->k2_skip ? k2.thresh * (1.f - 1.f / 8192.f) : -INFINITY;
     if (h->fast_k2) {
-        choose_k2_tiles(h, n, store, k2.tw, k2.th);
+        if (!choose_k2_tiles(h, n, store, k2.tw, k2.th)) {
+            set_err(&h->err, "no tile plan for the integer-scale peak kernel (tw=%d th=%d)", k2.tw, k2.th);
+            return OPP_ERR_INVALID;
+        }
         k2.nxs = (h->g.w + k2.tw - 1) / k2.tw, k2.nys = (h->g.h + k2.th - 1) / k2.th;
     }
     return OPP_OK;
@@ -1030,7 +1135,7 @@ int opp_peaks_device(opp_handle_t h, const float *conf, const float *paf, int n_
     cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
     CU(cudaMemsetAsync(s.d_counters, 0, h->counters_ints * sizeof(int), st));
     K2Params k2{};
-    fill_k2(h, s, conf, nullptr, n_frames, conf_up != nullptr, k2);
+    if (int r = fill_k2(h, s, conf, nullptr, n_frames, conf_up != nullptr, k2)) return r;
     if (conf_up) k2.paf = paf, k2.up_conf = conf_up, k2.up_paf = paf_up;
     CU(launch_k2_fast(k2, n_frames, st));
     h->launches += 1;

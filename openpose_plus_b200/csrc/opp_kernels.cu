@@ -474,8 +474,8 @@ __device__ __forceinline__ void col_all(const float *__restrict__ k, float a, fl
 }
 
 #ifndef K2_FAST_MAX_THREADS
-#define K2_FAST_MAX_WARPS 7       // column groups per CTA: 7 x 62 decided columns >= 432
-#define K2_FAST_MAX_THREADS 224
+#define K2_FAST_MAX_WARPS K2_FAST_MAX_GROUPS // column groups per CTA: 7 x 62 decided columns >= 432
+#define K2_FAST_MAX_THREADS (32 * K2_FAST_MAX_GROUPS)
 #define K2_FAST_MIN_CTAS 3
 #endif
 
@@ -1867,7 +1867,7 @@ static cudaError_t launch_k2_fast_t(const K2Params &p, int n_frames, size_t smem
     const int groups = (S * p.tw + 61) / 62;
     if (groups < 1 || groups > K2_FAST_MAX_WARPS || p.th + 4 > 64 || p.tw + 2 > 64) return cudaErrorInvalidValue; // 64-bit activity masks
     const int threads = 32 * groups;
-    if (STORE && 4 * p.tw > threads) return cudaErrorInvalidValue; // two threads per 16-byte column of the tile
+    if (STORE && 2 * ((S * p.tw) >> 2) > threads) return cudaErrorInvalidValue; // two threads per 16-byte column of the tile
     return launch_ex(k2_peaks_fast<S, R, STORE>, grid, dim3(threads), smem, st, pdl, p);
 }
 

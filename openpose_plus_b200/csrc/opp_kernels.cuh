@@ -8,6 +8,7 @@
 
 #define OPP_MAX_KSIZE 63
 #define OPP_THREADS 256
+#define K2_FAST_MAX_GROUPS 7 // column groups (warps) per CTA of the integer-scale peak kernel: 7 x 62 decided columns >= 432
 
 // Geometry shared by every stage.  S > 0 means both axes scale by the same integer factor
 // (every configuration in BASELINE.json is x8): INTER_AREA up-sampling is then exact pixel

@@ -29,8 +29,7 @@ class paf_processor_b200 : public paf_batch_processor
             // the reference exit(1)s on device errors (src/cudnn_traits.hpp:11-20); a constructor can throw instead
             throw std::runtime_error(std::string("create_paf_processor: ") + opp_last_error(nullptr));
         }
-        humans_.resize((size_t)cfg_.max_batch * cfg_.max_humans);
-        counts_.resize(cfg_.max_batch), flags_.resize(cfg_.max_batch);
+        size_buffers();
     }
 
     ~paf_processor_b200() override { opp_destroy(h_); }
@@ -52,6 +51,15 @@ class paf_processor_b200 : public paf_batch_processor
             b.in_mem = device_memory ? OPP_MEM_DEVICE : OPP_MEM_HOST, b.in_layout = OPP_LAYOUT_CHW, b.out_mem = OPP_MEM_HOST;
             b.humans = humans_.data(), b.n_humans = counts_.data(), b.frame_flags = flags_.data();
             if (opp_process(h_, &b) != OPP_OK) throw std::runtime_error(std::string("paf_processor: ") + opp_last_error(h_));
+            // The reference's vectors grow without bound (src/post-process.h:190-198, src/paf.cpp:117-131,237-247); this
+            // build works inside fixed capacities and flags a frame that exceeds one.  A caller of the reference's
+            // interface must never see a truncated result: grow the capacities and run the batch again.
+            int over = 0;
+            for (int f = 0; f < m; ++f) over |= flags_[f] & (OPP_FLAG_PEAK_OVERFLOW | OPP_FLAG_CAND_OVERFLOW | OPP_FLAG_HUMAN_OVERFLOW);
+            if (over) {
+                grow(over);
+                continue;
+            }
             for (int f = 0; f < m; ++f) {
                 std::vector<human_t> hs(counts_[f]);
                 if (counts_[f]) std::memcpy(static_cast<void *>(hs.data()), &humans_[(size_t)f * cfg_.max_humans], counts_[f] * sizeof(human_t));
@@ -63,6 +71,29 @@ class paf_processor_b200 : public paf_batch_processor
     }
 
   private:
+    void size_buffers()
+    {
+        humans_.resize((size_t)cfg_.max_batch * cfg_.max_humans);
+        counts_.resize(cfg_.max_batch), flags_.resize(cfg_.max_batch);
+    }
+
+    // doubles the capacities named by the overflow bits and re-creates the handle; throws when the device cannot hold them
+    void grow(int over)
+    {
+        opp_config_t c = cfg_;
+        if (over & OPP_FLAG_PEAK_OVERFLOW) c.max_peaks_per_part *= 2, c.max_cands_per_limb *= 4;
+        if (over & OPP_FLAG_CAND_OVERFLOW) c.max_cands_per_limb *= 2;
+        if (over & OPP_FLAG_HUMAN_OVERFLOW) c.max_humans *= 2;
+        opp_handle_t nh = nullptr;
+        if (opp_create(&c, &nh) != OPP_OK)
+            throw std::runtime_error(std::string("paf_processor: frame exceeds the capacities (peaks/part ") + std::to_string(cfg_.max_peaks_per_part) +
+                                     ", candidates/limb " + std::to_string(cfg_.max_cands_per_limb) + ", humans " + std::to_string(cfg_.max_humans) +
+                                     ") and they cannot grow: " + opp_last_error(nullptr));
+        opp_destroy(h_);
+        h_ = nh, cfg_ = c;
+        size_buffers();
+    }
+
     opp_config_t cfg_;
     opp_handle_t h_ = nullptr;
     std::vector<opp_human_t> humans_;

@@ -72,7 +72,8 @@ def humans_from_records(records, height, width):
 
 class PostProcessor(object):
     def __init__(self, origin_size, feature_size, data_format='channels_last', gauss_kernel_size=17, device=-1,
-                 return_maps=True, maps_on_device=False, max_batch=1, variant='cpp'):
+                 return_maps=True, maps_on_device=False, max_batch=1, variant='cpp', max_peaks_per_part=128,
+                 max_cands_per_limb=1024, max_humans=128):
         """origin_size: (height, width) the maps are up-sampled to; feature_size: (height', width') of
         the feature maps; data_format: 'channels_last' ([h, w, C]) or 'channels_first' ([C, h, w]).
         variant: 'cpp' (default) = the semantics of the reference's C++ path, src/paf.cpp (the parity target);
@@ -86,10 +87,31 @@ class PostProcessor(object):
         self.origin_size = tuple(origin_size)
         self.feature_size = tuple(feature_size)
         self.return_maps, self.maps_on_device = return_maps, maps_on_device
-        self.engine = Engine(feature_size[0], feature_size[1], origin_size[0], origin_size[1], gauss_kernel_size,
-                             max_batch=max_batch, device=device,
-                             variant=capi.VARIANT_PYTHON if variant == 'python' else capi.VARIANT_CPP)
+        self._engine_args = dict(gauss_kernel_size=gauss_kernel_size, max_batch=max_batch, device=device,
+                                 variant=capi.VARIANT_PYTHON if variant == 'python' else capi.VARIANT_CPP)
+        # starting capacities; they grow on demand (_grow) because the reference's containers are unbounded
+        self._caps = dict(max_peaks_per_part=max_peaks_per_part, max_cands_per_limb=max_cands_per_limb, max_humans=max_humans)
+        self.engine = self._make_engine()
         self._up = None
+
+    def _make_engine(self):
+        fs, os_ = self.feature_size, self.origin_size
+        return Engine(fs[0], fs[1], os_[0], os_[1], **self._engine_args, **self._caps)
+
+    def _grow(self, over):
+        """The reference's vectors are unbounded; this build flags a frame that exceeds a fixed capacity.  A caller of
+        the reference's interface must never get a truncated result: double what overflowed and run again."""
+        c = self._caps
+        if over & capi.FLAG_PEAK_OVERFLOW:
+            c['max_peaks_per_part'] *= 2
+            c['max_cands_per_limb'] *= 4
+        if over & capi.FLAG_CAND_OVERFLOW:
+            c['max_cands_per_limb'] *= 2
+        if over & capi.FLAG_HUMAN_OVERFLOW:
+            c['max_humans'] *= 2
+        old = self.engine
+        self.engine = self._make_engine()  # raises OppError when the device cannot hold these capacities
+        old.close()
 
     def close(self):
         self.engine.close()
@@ -110,7 +132,13 @@ class PostProcessor(object):
         if self.return_maps:
             cu, pu = self._maps(n)
             kw = dict(conf_up=cu, paf_up=pu, up_layout=capi.LAYOUT_HWC)
-        records, counts, flags = self.engine.process(heatmaps, pafmaps, layout=layout, **kw)
+        while True:
+            records, counts, flags = self.engine.process(heatmaps, pafmaps, layout=layout, **kw)
+            over = int(np.bitwise_or.reduce(flags)) & capi.FLAG_OVERFLOW_MASK if n else 0
+            if not over:
+                break
+            self._grow(over)
+        self.last_flags = flags
         H, W = self.origin_size
         humans = [humans_from_records(records[f, :counts[f]], H, W) for f in range(n)]
         if not self.return_maps:

@@ -36,7 +36,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts():
     assert capi.HUMAN_DT.itemsize == 292 and capi.PEAK_DT.itemsize == 20 and capi.CONN_DT.itemsize == 12
     assert C.sizeof(capi.Config) == 16 * 4
-    assert C.sizeof(capi.Batch) == 2 * 8 + 4 * 4 + 3 * 8 + 2 * 8 + 4 * 4
+    assert C.sizeof(capi.Batch) == 2 * 8 + 4 * 4 + 3 * 8 + 2 * 8 + 2 * 4 + 8
+    assert capi.Batch.in_sync_obj.offset == 80 and capi.Batch.in_sync.offset == 76 and capi.Batch.up_layout.offset == 72
 
 
 @pytest.mark.skipif(conftest.HAS_GPU, reason="only meaningful without a GPU")
@@ -300,3 +301,144 @@ def test_create_rejects_bad_configurations_before_touching_the_device():
     rc, msg = create()
     assert rc == (capi.OK if conftest.HAS_GPU else capi.ERR_NO_DEVICE), (rc, msg)
     assert L.opp_bench_latency(None, None, 1, None) == capi.ERR_INVALID
+
+
+REF_INC = "/root/reference/include"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_INC, "openpose-plus.hpp")), reason="reference headers only exist in the build container")
+def test_dropin_builds_against_the_unmodified_reference_headers(tmp_path):
+    """The ABI claim pinned in CI: a caller compiled with the reference's OWN headers links against libopp_b200.so
+    (factory signature, paf_processor vtable), and the structs those headers define have the layout the C-ABI writes."""
+    from openpose_plus_b200 import build as b
+    exe = b.build_dropin_against_reference_headers(force=True)
+    assert exe and os.path.exists(exe)
+    nm = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True).stdout
+    assert "create_paf_processor" in nm
+    probe = tmp_path / "abi.cpp"
+    probe.write_text(r"""
+#include <cstddef>
+#include <string>
+#include <openpose-plus.hpp>          // the reference's
+#include "opp_b200.h"                 // ours
+static_assert(sizeof(human_t) == sizeof(opp_human_t) && sizeof(human_t) == 292, "human_t");
+static_assert(sizeof(body_part_t) == sizeof(opp_body_part_t), "body_part_t");
+static_assert(offsetof(body_part_t, x) == offsetof(opp_body_part_t, x) && offsetof(body_part_t, score) == offsetof(opp_body_part_t, score), "part fields");
+static_assert(offsetof(human_t, score) == offsetof(opp_human_t, score), "human score");
+// vtable order of the interface the library implements: operator() first, then the destructors
+struct probe_impl : paf_processor {
+    std::vector<human_t> operator()(const float *, const float *, bool) override { return {}; }
+};
+int main() { probe_impl p; paf_processor *q = &p; return (int)(*q)(nullptr, nullptr, false).size(); }
+""")
+    r = subprocess.run(["g++", "-std=c++14", "-I", REF_INC, "-I", os.path.join(ROOT, "include"), str(probe), "-o", str(tmp_path / "abi")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # the re-written headers this repo ships declare the same interface (incl. the out-of-scope runner, declaration only)
+    ours = open(os.path.join(ROOT, "include", "openpose-plus.hpp")).read()
+    assert "class pose_detection_runner" in ours and "create_pose_detection_runner(" in ours
+
+
+def test_shipped_header_lets_a_runner_translation_unit_compile(tmp_path):
+    """with this repo's include/ first on the path, code that implements or calls the reference's
+    pose_detection_runner (src/uff-runner.cpp, examples/*.cpp) still compiles."""
+    src = tmp_path / "runner.cpp"
+    src.write_text(r"""
+#include <openpose-plus.h>
+struct fake_runner : pose_detection_runner {
+    void operator()(const std::vector<void *> &, const std::vector<void *> &, int) override {}
+};
+pose_detection_runner *create_pose_detection_runner(const std::string &, int, int, int, bool) { return new fake_runner; }
+int main() { delete create_pose_detection_runner("m.uff", 368, 432, 1, false); return 0; }
+""")
+    r = subprocess.run(["g++", "-std=c++14", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(tmp_path / "runner")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(tmp_path / "runner")]).returncode == 0
+
+
+def test_tranform_keypoints2d_matches_the_reference_helper():
+    """openpose_plus/inference/common.py:86-96 (name sic): pixel coordinates, scores, visibility above the threshold."""
+    from openpose_plus_b200.common import tranform_keypoints2d
+    from openpose_plus_b200.post_process import BodyPart
+    body = {0: BodyPart("0-0", 0, 0.5, 0.25, 0.9), 7: BodyPart("0-7", 7, 0.1, 0.75, 0.2), 17: BodyPart("0-17", 17, 1.0, 1.0, 0.25)}
+    xy, conf, vis = tranform_keypoints2d(body, 432, 368)
+    assert xy.shape == (18, 2) and conf.shape == (18,) and vis.dtype == bool
+    assert xy[0].tolist() == [216.0, 92.0] and xy[7].tolist() == [0.1 * 432, 0.75 * 368] and xy[3].tolist() == [0.0, 0.0]
+    assert conf[0] == 0.9 and conf[7] == 0.2 and conf[1] == 0
+    assert vis.tolist() == [i == 0 for i in range(18)]          # 0.25 is not above the default threshold
+    assert tranform_keypoints2d(body, 432, 368, kp_score_thresh=0.1)[2].sum() == 3
+
+
+def test_dlpack_intake_validates_and_consumes():
+    """north_star: 'numpy or DLPack buffers'.  Capsules are consumed through the CPython capsule API (no torch import
+    inside the package), validated (device / dtype / compact strides) and handed back to the producer on release."""
+    import gc
+    import torch
+    from openpose_plus_b200 import dlpack
+    t = torch.arange(2 * 19 * 4 * 6, dtype=torch.float32).reshape(2, 19, 4, 6)
+    b = dlpack.resolve(t, "conf", dlpack.F32)
+    assert b.ptr == t.data_ptr() and b.shape == (2, 19, 4, 6) and b.nbytes == t.numel() * 4 and not b.on_device
+    b.release()
+    b.release()                                                       # idempotent
+    sl = dlpack.resolve(t[1:], "conf", dlpack.F32)                    # contiguous slice: byte offset / data pointer honoured
+    assert sl.ptr == t[1:].data_ptr() and sl.shape == (1, 19, 4, 6)
+    cap = t.__dlpack__()                                              # a ready capsule (what a C++ producer would hand over)
+    assert dlpack.resolve(cap, "conf", dlpack.F32).ptr == t.data_ptr()
+    with pytest.raises(TypeError):
+        dlpack.resolve(cap, "conf", dlpack.F32)                       # already consumed
+    a = np.zeros((3, 5), np.float32)
+    assert dlpack.from_dlpack(a, "a", dlpack.F32).ptr == a.ctypes.data  # numpy speaks DLPack too
+    for bad in (t[:, :, ::2], t.transpose(2, 3), t.double(), t.half(), t.int()):
+        with pytest.raises(TypeError):
+            dlpack.resolve(bad, "conf", dlpack.F32)
+    with pytest.raises(TypeError):
+        dlpack.resolve(np.zeros((4, 4), np.float32)[:, ::2], "x", dlpack.F32)
+    with pytest.raises(TypeError):
+        dlpack.resolve("not a buffer", "x")
+    assert dlpack.resolve(torch.zeros(4, dtype=torch.int32), "n", dlpack.I32).nbytes == 16
+    # the producer gets its tensor back: nothing keeps the storage alive after release
+    import weakref
+    u = torch.zeros(1000)
+    ref = weakref.ref(u.untyped_storage())
+    bu = dlpack.resolve(u, "u")
+    del u
+    gc.collect()
+    assert ref() is not None                                          # the consumed capsule owns a reference
+    bu.release()
+    del bu
+    gc.collect()
+    assert ref() is None
+
+
+def test_engine_rejects_wrong_shapes_dtypes_and_strides_before_the_c_abi():
+    """The C-ABI takes raw pointers: the Python host side refuses anything it cannot vouch for (a non-contiguous
+    or fp16 device tensor gave wrong skeletons silently)."""
+    import torch
+    from openpose_plus_b200.engine import Engine
+    e = object.__new__(Engine)                                        # host-side checks only: no device, no handle
+    e.feat, e.out, e.max_humans, e.device = (4, 6), (32, 48), 8, 0
+    ok = np.zeros((2, 19, 4, 6), np.float32)
+    a, ptr, n, dev = e._map_in(ok, 19, "conf", capi.LAYOUT_CHW)
+    assert ptr == ok.ctypes.data and n == 2 and not dev
+    a, ptr, n, dev = e._map_in(ok.astype(np.float64)[:, :, ::1], 19, "conf", capi.LAYOUT_CHW)   # numpy inputs are normalised
+    assert a.dtype == np.float32 and ptr == a.ctypes.data
+    assert e._map_in(np.zeros((2, 4, 6, 38), np.float32), 38, "paf", capi.LAYOUT_HWC)[2] == 2
+    for bad in (np.zeros((2, 19, 4, 5), np.float32), np.zeros((19, 4, 6), np.float32), np.zeros((2, 38, 4, 6), np.float32)):
+        with pytest.raises(capi.OppError):
+            e._map_in(bad, 19, "conf", capi.LAYOUT_CHW)
+    t = torch.zeros(2, 19, 4, 6)
+    assert e._map_in(t, 19, "conf", capi.LAYOUT_CHW)[1] == t.data_ptr()
+    for bad in (t.half(), t.double(), torch.zeros(2, 19, 4, 12)[..., ::2], torch.zeros(2, 19, 6, 4).transpose(2, 3)):
+        with pytest.raises(capi.OppError):
+            e._map_in(bad, 19, "conf", capi.LAYOUT_CHW)
+    humans = np.zeros((2, 8), capi.HUMAN_DT)
+    assert e._buf_out(humans, "humans", 2 * 8 * 292)[1] == humans.ctypes.data
+    with pytest.raises(capi.OppError):
+        e._buf_out(humans[:1], "humans", 2 * 8 * 292)                 # too small
+    with pytest.raises(capi.OppError):
+        e._buf_out(np.zeros(2, np.int64), "n_humans", 8, 4)           # wrong element size
+    with pytest.raises(capi.OppError):
+        e._buf_out(np.zeros((2, 19, 32, 48), np.float32), "conf_up", 4, device_only=True)   # up-sampled maps are device buffers
+    ro = np.zeros(2, np.int32)
+    ro.flags.writeable = False
+    with pytest.raises(capi.OppError):
+        e._buf_out(ro, "n_humans", 8, 4)
