@@ -223,6 +223,12 @@ int opp_draw_human(uint8_t *image, int height, int width, int channels, ptrdiff_
  * the interpreter overhead a Python loop adds to every call.  Returns the status of the first failing call. */
 int opp_bench_latency(opp_handle_t h, const opp_batch_t *batch, int iters, float *out_us);
 
+/* Host->device ceiling of this handle's input path, nothing else: `iters` times the same two cudaMemcpyAsync calls
+ * opp_submit issues for a host batch of n_frames (conf, paf -> the slots' staging buffers, on the slots' streams), no
+ * kernels; conf / paf hold n_batches consecutive batches that are cycled through; *out_ms = CUDA-event time over all
+ * slot streams.  bench.py runs it on every rank at once to put a measured PCIe ceiling beside the end-to-end number. */
+int opp_bench_h2d(opp_handle_t h, const float *conf, const float *paf, int n_frames, int n_batches, int iters, float *out_ms);
+
 const char *opp_last_error(opp_handle_t h);
 const char *opp_version(void);
 

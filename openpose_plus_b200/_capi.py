@@ -93,6 +93,7 @@ def lib():
         L.opp_last_error.restype = C.c_char_p
         L.opp_version.restype = C.c_char_p
         L.opp_bench_latency.argtypes = [C.c_void_p, C.POINTER(Batch), C.c_int, C.c_void_p]
+        L.opp_bench_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.opp_draw_human.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_ssize_t, C.c_void_p, C.c_int]
         _lib = L
     return _lib
@@ -101,7 +102,7 @@ def lib():
 EXPORTS = ["opp_config_default", "opp_create", "opp_destroy", "opp_process", "opp_submit", "opp_wait",
            "opp_last_batch_ms", "opp_launch_count", "opp_device", "opp_host_alloc", "opp_host_free", "opp_host_alloc_ex",
            "opp_host_register", "opp_host_unregister", "opp_stream_wait_ticket", "opp_debug_fetch",
-           "opp_resize_device", "opp_resize_pair_device", "opp_peaks_device", "opp_timer_start", "opp_timer_stop", "opp_last_error", "opp_version", "opp_draw_human", "opp_bench_latency", "process_conf_paf"]
+           "opp_resize_device", "opp_resize_pair_device", "opp_peaks_device", "opp_timer_start", "opp_timer_stop", "opp_last_error", "opp_version", "opp_draw_human", "opp_bench_latency", "opp_bench_h2d", "process_conf_paf"]
 
 
 def pinned_empty(shape, dtype, write_combined=False):

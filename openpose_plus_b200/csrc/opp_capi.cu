@@ -36,6 +36,7 @@ struct Slot {
     cudaStream_t side = nullptr; // materialising resize runs beside peak finding / grouping
     cudaEvent_t ev_start = nullptr, ev_done = nullptr, ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_in = nullptr; // recorded on the producer's stream (OPP_SYNC_STREAM)
+    cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr; // OPP_H2D_SPLIT: the PAF copy runs on the side stream
     cudaEvent_t tr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // OPP_TRACE: k1 start/end, k2 start/end, k3 end, copies end
     // device arena
     float *d_conf = nullptr, *d_paf = nullptr; // staged feature maps [B,19,h,w] / [B,38,h,w]
@@ -103,6 +104,7 @@ struct opp_handle_s {
     bool stage_pageable = true; // latency path for pageable inputs through pinned staging (OPP_NO_STAGE_PAGEABLE=1: cudaMemcpyAsync from pageable memory)
     bool pdl = true; // programmatic dependent launch on the latency path (OPP_NO_PDL=1 disables)
     int zero_copy_in_max = 0; // kernels reading pinned host maps in place: measured slower than staging them (kept for experiments)
+    bool h2d_split = false;   // OPP_H2D_SPLIT=1: the two input tensors of a batch are copied on two streams (measured: no gain, see DESIGN)
     int ingest_max = 4;       // up to this many frames, pinned host maps are pulled in by one kernel instead of memset + 2 DMA copies
     cudaEvent_t trace_base = nullptr;
 };
@@ -250,6 +252,8 @@ int free_slot(opp_handle_s *h, Slot &s)
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
     if (s.ev_join) cudaEventDestroy(s.ev_join);
     if (s.ev_in) cudaEventDestroy(s.ev_in);
+    if (s.ev_h2d0) cudaEventDestroy(s.ev_h2d0);
+    if (s.ev_h2d1) cudaEventDestroy(s.ev_h2d1);
     if (s.side) cudaStreamDestroy(s.side);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
@@ -274,6 +278,8 @@ int alloc_slot(opp_handle_s *h, Slot &s)
     CU(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.ev_h2d0, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.ev_h2d1, cudaEventDisableTiming));
     if (h->trace) {
         for (auto &e : s.tr) CU(cudaEventCreate(&e));
         CU(cudaMalloc(&s.d_times, (B * OPP_N_PAIRS * 12 + 4096 * 8) * sizeof(unsigned long long)));
@@ -581,6 +587,8 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
         h->paf_early = getenv("OPP_NO_PAF_EARLY") == nullptr;
         if (const char *e = getenv("OPP_ZC_IN_MAX")) h->zero_copy_in_max = atoi(e);
         if (const char *e = getenv("OPP_INGEST_MAX")) h->ingest_max = atoi(e);
+        if (h->ingest_max > c.max_batch) h->ingest_max = c.max_batch;
+        h->h2d_split = getenv("OPP_H2D_SPLIT") != nullptr;
         CU(cudaStreamCreateWithFlags(&h->timer_stream, cudaStreamNonBlocking));
         if (h->trace) {
             CU(cudaEventCreate(&h->trace_base));
@@ -688,8 +696,17 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
         // (each feature row is staged into shared memory once per tile anyway); no copy is enqueued
         conf = (const float *)mapped_host(b.conf), paf = (const float *)mapped_host(b.paf);
     } else if (b.in_mem == OPP_MEM_HOST) {
-        CU(cudaMemcpyAsync(s.d_conf, b.conf, n * OPP_N_HEAT * hw * sizeof(float), in_kind, st));
-        CU(cudaMemcpyAsync(s.d_paf, b.paf, n * OPP_N_PAF * hw * sizeof(float), in_kind, st));
+        if (h->h2d_split) { // experiment: heat maps and PAFs on two copy streams at once
+            CU(cudaEventRecord(s.ev_h2d0, st));
+            CU(cudaStreamWaitEvent(s.side, s.ev_h2d0, 0));
+            CU(cudaMemcpyAsync(s.d_paf, b.paf, n * OPP_N_PAF * hw * sizeof(float), in_kind, s.side));
+            CU(cudaEventRecord(s.ev_h2d1, s.side));
+            CU(cudaMemcpyAsync(s.d_conf, b.conf, n * OPP_N_HEAT * hw * sizeof(float), in_kind, st));
+            CU(cudaStreamWaitEvent(st, s.ev_h2d1, 0));
+        } else {
+            CU(cudaMemcpyAsync(s.d_conf, b.conf, n * OPP_N_HEAT * hw * sizeof(float), in_kind, st));
+            CU(cudaMemcpyAsync(s.d_paf, b.paf, n * OPP_N_PAF * hw * sizeof(float), in_kind, st));
+        }
         conf = s.d_conf, paf = s.d_paf;
     } else {
         conf = b.conf, paf = b.paf; // device-resident feature maps are used in place
@@ -1028,6 +1045,25 @@ float opp_last_batch_ms(opp_handle_t h, int ticket)
         s->ms_pending = false;
     }
     return s->last_ms;
+}
+
+int opp_bench_h2d(opp_handle_t h, const float *conf, const float *paf, int n_frames, int n_batches, int iters, float *out_ms)
+{
+    if (!h || !conf || !paf || !out_ms || iters < 1 || n_batches < 1 || n_frames < 1 || n_frames > h->cfg.max_batch) return OPP_ERR_INVALID;
+    DeviceGuard guard_(h->device);
+    for (auto &s : h->slots)
+        if (s.busy) return OPP_ERR_BUSY;
+    const size_t hw = (size_t)h->g.h * h->g.w;
+    int rc = opp_timer_start(h);
+    if (rc != OPP_OK) return rc;
+    for (int i = 0; i < iters; ++i) {
+        Slot &s = h->slots[i % h->slots.size()];
+        const size_t k = (size_t)(i % n_batches) * n_frames; // distinct host batches: the host side must not be served from its caches
+        CU(cudaMemcpyAsync(s.d_conf, conf + k * OPP_N_HEAT * hw, n_frames * OPP_N_HEAT * hw * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(s.d_paf, paf + k * OPP_N_PAF * hw, n_frames * OPP_N_PAF * hw * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+    }
+    *out_ms = opp_timer_stop(h);
+    return *out_ms < 0.f ? OPP_ERR_CUDA : OPP_OK;
 }
 
 int64_t opp_launch_count(opp_handle_t h) { return h ? h->launches : 0; }

@@ -222,6 +222,8 @@ class Reference:
             L.ref_time_frames.restype = C.c_double
             L.ref_time_frames.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
             L.ref_std_sort_desc.argtypes = [C.c_void_p, C.c_int]
+            L.ref_latency_frames.restype = None
+            L.ref_latency_frames.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
             L.ref_pool_create.restype = C.c_void_p
             L.ref_pool_create.argtypes = [C.c_int] * 6
             L.ref_pool_destroy.argtypes = [C.c_void_p]
@@ -247,6 +249,14 @@ class Reference:
         n = self.L.ref_run(self.p, pc, pp, out.ctypes.data, cap)
         assert n <= cap
         return out[:n].copy()
+
+    def latency_ms(self, conf, paf, iters):
+        """Per-call wall time (ms) of `iters` one-frame calls on this processor, one thread, stdout silenced."""
+        conf, pc = _f32(conf)
+        paf, pp = _f32(paf)
+        out = np.zeros(iters, np.float64)
+        self.L.ref_latency_frames(self.p, pc, pp, conf.shape[0], self.geom[0], self.geom[1], iters, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
 
     @classmethod
     def time_frames(cls, geom, conf, paf, repeat=1, threads=1, fast=True):

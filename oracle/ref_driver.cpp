@@ -96,6 +96,22 @@ double ref_time_frames(int feat_h, int feat_w, int out_h, int out_w, int ksize, 
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// One processor, one thread, one frame per call: the latency a caller of the reference's paf_processor sees
+// (single-thread ms per frame, p50).  out_ms[iters] receives every call's wall time.
+void ref_latency_frames(void *p, const float *conf, const float *paf, int n_frames, int feat_h, int feat_w, int iters, double *out_ms)
+{
+    stdout_silencer quiet;
+    const size_t cs = (size_t)19 * feat_h * feat_w, ps = (size_t)38 * feat_h * feat_w;
+    paf_processor *proc = static_cast<paf_processor *>(p);
+    for (int i = 0; i < iters; ++i) {
+        const int f = i % n_frames;
+        const auto t0 = std::chrono::steady_clock::now();
+        const size_t n = (*proc)(conf + f * cs, paf + f * ps, false).size();
+        const auto t1 = std::chrono::steady_clock::now();
+        out_ms[i] = std::chrono::duration<double, std::milli>(t1 - t0).count() + 0.0 * (double)n;
+    }
+}
+
 // A pool of processors kept across calls (constructing one allocates ~100 MB of scratch, which
 // is setup, not per-frame work): ref_pool_run times n_frames on the pool's threads.
 struct ref_pool {

@@ -132,7 +132,7 @@ dist.init_process_group("gloo")
 n = 37
 lo, hi = shard_range(n, rank, world)
 humans = np.zeros((hi - lo, 4), capi.HUMAN_DT)
-counts = np.arange(lo, hi, dtype=np.int32) % 4
+counts = (np.arange(lo, hi, dtype=np.int32) % 4).clip(1)     # only the humans found travel: slot 0 must be one of them
 flags = np.zeros(hi - lo, np.int32)
 for f in range(lo, hi):
     humans[f - lo]["score"] = f          # frame index rides in the payload
@@ -140,7 +140,7 @@ res = gather_results((humans, counts, flags), rank, world)
 if rank == 0:
     H, Cn, F = res
     assert H.shape == (n, 4) and np.array_equal(H["score"][:, 0], np.arange(n, dtype=np.float32))
-    assert np.array_equal(Cn, np.arange(n, dtype=np.int32) % 4)
+    assert np.array_equal(Cn, (np.arange(n, dtype=np.int32) % 4).clip(1))
     print("GATHER_OK")
 else:
     assert res is None
@@ -442,3 +442,72 @@ def test_engine_rejects_wrong_shapes_dtypes_and_strides_before_the_c_abi():
     ro.flags.writeable = False
     with pytest.raises(capi.OppError):
         e._buf_out(ro, "n_humans", 8, 4)
+
+
+_SHM_WORKER = r"""
+import os, sys, time
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from openpose_plus_b200.sharding import HostGather, process_stream, shard_range
+from test_capi_and_host import _FakeEngine
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")                       # only for the final cross-check; the gather itself is shared memory
+n = 53
+conf = np.zeros((n, 19, 2, 2), np.float32)
+conf[:, 0, 0, 0] = np.arange(n) % 4                   # "humans found" per frame rides in the payload
+paf = np.zeros((n, 38, 2, 2), np.float32)
+g = HostGather("opp_test_gather_%s" % os.environ["MASTER_PORT"], n, 4, rank, world, register=False)
+lo, hi = shard_range(n, rank, world)
+for rnd in range(3):                                  # three passes over the stream through the same segment
+    if rnd:
+        g.wait_released() if rank else None
+    eng = _FakeEngine()
+    if rnd == 1:                                      # a rank that only HOLDS its shard
+        res = process_stream(eng, conf[lo:hi], paf[lo:hi], rank, world, gather=g, shard_only=True)
+    else:
+        res = process_stream(eng, conf, paf, rank, world, gather=g)
+    assert sum(c[0].shape[0] for c in eng.calls) == hi - lo
+    if rank == 0:
+        H, Cn, F = res
+        assert Cn.tolist() == (np.arange(n) % 4).tolist() and H["score"][:, 0].tolist() == (np.arange(n) % 4).astype(float).tolist()
+        H["score"][:] = -1                            # consumed; the next round must rewrite every frame
+        Cn[:] = -1
+        g.release()
+    else:
+        assert res is None
+dist.barrier()
+g.close()
+if rank == 0:
+    assert not os.path.exists("/dev/shm/opp_test_gather_%s" % os.environ["MASTER_PORT"])
+    print("SHM_GATHER_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_shared_memory_host_gather_world_size_2(tmp_path):
+    """configs[4]'s host gather as bench.py runs it: every rank writes its shard's results into one shared segment and
+    rank 0 sees the stream in frame order after a sequence-number handshake - no copy, no collective."""
+    w = tmp_path / "worker.py"
+    w.write_text(_SHM_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29741", str(w), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "SHM_GATHER_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_gather_results_ships_only_the_humans_found():
+    from openpose_plus_b200.sharding import _compact, _expand
+    hh = np.zeros((5, 4), capi.HUMAN_DT)
+    hh["score"] = np.arange(20).reshape(5, 4)
+    cc = np.array([0, 1, 4, 2, 9], np.int32)              # 9 > capacity: an overflowed frame keeps its 4 slots
+    recs, c2, f2, cap = _compact((hh, cc, cc))
+    assert len(recs) == 0 + 1 + 4 + 2 + 4 and cap == 4
+    back = _expand((recs, c2, f2, cap))
+    want = hh.copy()
+    for f in range(5):
+        want["score"][f, min(cc[f], 4):] = 0
+    assert np.array_equal(back[0]["score"], want["score"]) and np.array_equal(back[1], cc)
+    empty = _expand(_compact((np.zeros((0, 4), capi.HUMAN_DT), np.zeros(0, np.int32), np.zeros(0, np.int32))))
+    assert empty[0].shape == (0, 4)
