@@ -167,6 +167,11 @@ float opp_last_batch_ms(opp_handle_t h, int ticket);
 int opp_device(opp_handle_t h);
 /* Number of kernel launches issued by this handle so far. */
 int64_t opp_launch_count(opp_handle_t h);
+/* Which peak kernel opp_create selected for this geometry and kernel size (a static string):
+ *   "fast"        integer scale 8 or 4, Gaussian radius <= 2 x scale (k <= 33 at x8): reads the feature maps only
+ *   "generic_rep" any other integer scale / larger kernels: replication-aware, reads the feature maps only
+ *   "generic"     non-integer scales: 2-tap area-mode samples of the feature maps, staged per tile */
+const char *opp_peak_kernel(opp_handle_t h);
 
 /* Pinned host memory for opp_batch_t host buffers (pageable memory also works, slower). */
 void *opp_host_alloc(size_t bytes);

@@ -341,16 +341,18 @@ void *mapped_host(const void *p)
     return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
-// Tile plan of the integer-scale peak kernel.  Limits of the kernel itself (k2_peaks_fast / launch_k2_fast_t): a column
-// strip holds at most 62 feature columns (+2 halo columns in the 64-bit activity masks) and at most 7 warps x 62 decided
-// image columns; a row tile at most 60 feature rows (+4 halo rows).  Returns false when no valid plan exists for this
+// Tile plan of the integer-scale peak kernel.  Limits of the kernel itself (k2_peaks_fast / launch_k2_fast_t), with nb =
+// 1 (R <= S) or 2 (S < R <= 2S) cells of filter reach: a column strip holds at most 64 - 2 nb feature columns (+2 nb halo
+// columns in the 64-bit activity masks) and at most 7 warps x 62 decided image columns; a row tile at most 62 - 2 nb
+// feature rows (+2 + 2 nb halo rows).  Returns false when no valid plan exists for this
 // geometry (opp_create then selects the replication-aware generic kernel instead of failing at launch time).
 bool choose_k2_tiles(opp_handle_s *h, int n_frames, bool store, int &tw, int &th)
 {
     const OppGeom &g = h->g;
     const int S = g.S > 0 ? g.S : 1;
+    const int nb = g.R > S ? 2 : 1; // neighbour depth of the filter window (cells)
     int tw_max = (62 * K2_FAST_MAX_GROUPS) / S;
-    if (tw_max > 62) tw_max = 62;
+    if (tw_max > 64 - 2 * nb) tw_max = 64 - 2 * nb;
     if (tw_max < 1) return false;
     const int nxs = (g.w + tw_max - 1) / tw_max;
     tw = (g.w + nxs - 1) / nxs;
@@ -361,14 +363,14 @@ bool choose_k2_tiles(opp_handle_s *h, int n_frames, bool store, int &tw, int &th
     const int target = store ? 8 : 23;
     const int nys = (g.h + target - 1) / target;
     th = (g.h + nys - 1) / nys;
-    while ((k2_fast_smem_bytes(g, tw, th) > (size_t)72 * 1024 || th > 60) && th > 4) th = (th + 1) / 2;
+    while ((k2_fast_smem_bytes(g, tw, th) > (size_t)72 * 1024 || th > 62 - 2 * nb) && th > 4) th = (th + 1) / 2;
     // small batches: split rows too until the grid covers the chip about twice
     const long want = 2L * h->sm_count;
     while ((long)n_frames * OPP_N_PARTS * ((g.w + tw - 1) / tw) * ((g.h + th - 1) / th) < want && th > 6) th = (th + 1) / 2;
     if (h->force_tw > 0) tw = h->force_tw;
     if (h->force_th > 0) th = h->force_th;
     const int groups = (S * tw + 61) / 62;
-    return tw >= 1 && th >= 1 && tw + 2 <= 64 && th + 4 <= 64 && groups >= 1 && groups <= K2_FAST_MAX_GROUPS &&
+    return tw >= 1 && th >= 1 && tw + 2 * nb <= 64 && th + 2 + 2 * nb <= 64 && groups >= 1 && groups <= K2_FAST_MAX_GROUPS &&
            k2_fast_smem_bytes(g, tw, th) <= (size_t)h->max_smem - 1024;
 }
 
@@ -557,8 +559,8 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
         CU(cudaMemcpy(h->d_alpha, al.data(), al.size() * sizeof(float), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(h->d_beta, be.data(), be.size() * sizeof(float), cudaMemcpyHostToDevice));
         g.xofs = h->d_xofs, g.yofs = h->d_yofs, g.alpha = h->d_alpha, g.beta = h->d_beta;
-        // the fast kernel hard-wires cv::GaussianBlur's REFLECT_101 border and symmetric tap reuse
-        h->fast_k2 = k2_fast_supported(g) && c.variant == OPP_VARIANT_CPP;
+        // cv::GaussianBlur's REFLECT_101 border for every k the fast kernel covers; the Python graph's zero border at its k = 25
+        h->fast_k2 = k2_fast_supported(g, c.variant == OPP_VARIANT_PYTHON);
         if (const char *e = getenv("OPP_FORCE_GENERIC")) {
             if (atoi(e)) h->fast_k2 = false;
         }
@@ -1067,6 +1069,13 @@ int opp_bench_h2d(opp_handle_t h, const float *conf, const float *paf, int n_fra
 }
 
 int64_t opp_launch_count(opp_handle_t h) { return h ? h->launches : 0; }
+
+const char *opp_peak_kernel(opp_handle_t h)
+{
+    if (!h) return "";
+    if (h->fast_k2) return "fast";
+    return h->g.S > 0 && h->generic_rep ? "generic_rep" : "generic";
+}
 
 int opp_device(opp_handle_t h) { return h ? h->device : -1; }
 

@@ -409,42 +409,86 @@ __device__ __forceinline__ void emit_peak(const K2Params &p, int frame, int part
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 fast path: integer scale S, Gaussian radius R <= S.
+// K2 fast path: integer scale S, Gaussian radius R <= 2S.
 //
 // The up-sampled map is S x S blocks of one feature value, so
 //   * the row pass of cv::GaussianBlur only has h distinct input rows (not H): it is evaluated once
 //     per feature row into shared memory (Rrow[h][W]);
-//   * inside one feature row/column the 2R+1 taps touch only three distinct neighbours (a, b, c), so
-//     the tap products are shared between the S phases.  Every product and every sum is still the
-//     same IEEE operation on the same operands in the same order as OpenCV's scalar filter
-//     (row: s = k0*x0; s += kj*xj left to right;  column: s = kR*x; s += k(R+j)*(x[+j] + x[-j])),
+//   * inside one feature row/column the 2R+1 taps touch only three distinct neighbours (a, b, c) when
+//     R <= S and five (a2, a, b, c, c2) when S < R <= 2S (k = 19..33 at x8: the Python graph's fixed
+//     k = 25 among them), so the tap products are shared between the S phases.  Every product and
+//     every sum is still the same IEEE operation on the same operands in the same order as OpenCV's
+//     scalar filter (row: s = k0*x0; s += kj*xj left to right;  column: s = kR*x; s += k(R+j)*(x[+j] + x[-j])),
 //     so the smoothed map is bit-identical; it never exists in HBM.
-// BORDER_REFLECT_101 at the image edge maps onto the same three neighbours except for the single
-// tap at distance exactly S (only when R == S), handled by the *_sp operands.
+// The border rule only changes WHICH neighbour a tap reads (make_win): BORDER_REFLECT_101 at the image
+// edge maps onto the same neighbours except for the single taps at distance exactly S and 2S (the *s
+// operands); the Python graph's 'SAME' zero padding (BZ) makes the cells beyond the edge read 0.
+// tests/test_fast_kernel_model.py is the executable CPU model of exactly this operand scheme.
 // ------------------------------------------------------------------------------------------------
-template <int S, int R>
-__device__ __forceinline__ void row_taps(const float *__restrict__ k, float a, float b, float c, float a_sp, float c_sp,
-                                         float (&out)[S])
+struct Win9 {
+    float a2s, a2, as, a, b, c, cs, c2, c2s;
+};
+
+// Operands for cell i of n along one axis: (m2, m1, z, p1, p2) = cells i-2 .. i+2 (anything where the cell does
+// not exist: such a value is never selected).  NB = neighbour depth (1: R <= S, 2: S < R <= 2S; needs n >= NB + 1).
+template <int NB, bool BZ>
+__device__ __forceinline__ Win9 make_win(float m2, float m1, float z, float p1, float p2, int i, int n)
 {
-    // value of the up-sampled row at offset o from the start of this feature column (o in [-R, S-1+R])
-    auto src = [&](int o) -> float {
-        if (o < 0) return (R == S && o == -S) ? a_sp : a;
-        if (o < S) return b;
-        return (R == S && o == 2 * S - 1) ? c_sp : c;
-    };
+    Win9 v;
+    const bool lo1 = i > 0, hi1 = i < n - 1;
+    v.b = z;
+    if (BZ) {
+        v.a = v.as = lo1 ? m1 : 0.f;
+        v.c = v.cs = hi1 ? p1 : 0.f;
+    } else {
+        v.a = lo1 ? m1 : z, v.as = lo1 ? m1 : p1;
+        v.c = hi1 ? p1 : z, v.cs = hi1 ? p1 : m1;
+    }
+    if (NB > 1) {
+        const bool lo2 = i > 1, hi2 = i < n - 2;
+        if (BZ) {
+            v.a2 = v.a2s = lo2 ? m2 : 0.f;
+            v.c2 = v.c2s = hi2 ? p2 : 0.f;
+        } else {
+            v.a2 = lo2 ? m2 : (lo1 ? m1 : p1), v.a2s = lo2 ? m2 : (lo1 ? z : p2);
+            v.c2 = hi2 ? p2 : (hi1 ? p1 : m1), v.c2s = hi2 ? p2 : (hi1 ? z : m2);
+        }
+    } else {
+        v.a2 = v.a2s = v.c2 = v.c2s = 0.f;
+    }
+    return v;
+}
+
+// value of the replicated line at offset o from the start of the cell (o in [-2S, 3S-1]; o is a
+// compile-time constant at every call site once the loops are unrolled)
+template <int S>
+__device__ __forceinline__ float win_src(const Win9 &v, int o)
+{
+    if (o >= 0 && o < S) return v.b;
+    if (o < 0) {
+        const int d = -o;
+        return d < S ? v.a : (d == S ? v.as : (d < 2 * S ? v.a2 : v.a2s));
+    }
+    const int d = o - S + 1;
+    return d < S ? v.c : (d == S ? v.cs : (d < 2 * S ? v.c2 : v.c2s));
+}
+
+template <int S, int R, bool BZ>
+__device__ __forceinline__ void row_taps(const float *__restrict__ k, const Win9 &v, float (&out)[S])
+{
 #pragma unroll
     for (int q = 0; q < S; ++q) {
         float s;
-        if (R == 1) { // OpenCV's SymmRowSmallFilter, ksize 3
-            s = __fadd_rn(__fmul_rn(src(q), k[1]), __fmul_rn(__fadd_rn(src(q - 1), src(q + 1)), k[2]));
-        } else if (R == 2) { // ksize 5
-            s = __fadd_rn(__fmul_rn(src(q), k[2]), __fmul_rn(__fadd_rn(src(q - 1), src(q + 1)), k[3]));
-            s = __fadd_rn(s, __fmul_rn(__fadd_rn(src(q - 2), src(q + 2)), k[4]));
+        if (R == 1 && !BZ) { // OpenCV's SymmRowSmallFilter, ksize 3
+            s = __fadd_rn(__fmul_rn(win_src<S>(v, q), k[1]), __fmul_rn(__fadd_rn(win_src<S>(v, q - 1), win_src<S>(v, q + 1)), k[2]));
+        } else if (R == 2 && !BZ) { // ksize 5
+            s = __fadd_rn(__fmul_rn(win_src<S>(v, q), k[2]), __fmul_rn(__fadd_rn(win_src<S>(v, q - 1), win_src<S>(v, q + 1)), k[3]));
+            s = __fadd_rn(s, __fmul_rn(__fadd_rn(win_src<S>(v, q - 2), win_src<S>(v, q + 2)), k[4]));
         } else { // RowFilter: taps left to right
             s = 0.f;
 #pragma unroll
             for (int j = 0; j <= 2 * R; ++j) {
-                const float pr = __fmul_rn(k[j], src(q + j - R));
+                const float pr = __fmul_rn(k[j], win_src<S>(v, q + j - R));
                 s = (j == 0) ? pr : __fadd_rn(s, pr);
             }
         }
@@ -453,24 +497,19 @@ __device__ __forceinline__ void row_taps(const float *__restrict__ k, float a, f
 }
 
 template <int S, int R>
-__device__ __forceinline__ float col_phase(const float *__restrict__ k, const int ph, float a, float b, float c, float a_sp,
-                                           float c_sp)
+__device__ __forceinline__ float col_phase(const float *__restrict__ k, const int ph, const Win9 &v)
 {
-    float s = __fmul_rn(k[R], b);
+    float s = __fmul_rn(k[R], v.b);
 #pragma unroll
-    for (int j = 1; j <= R; ++j) {
-        const float up = (ph + j < S) ? b : ((R == S && ph == S - 1 && j == R) ? c_sp : c);
-        const float dn = (ph - j >= 0) ? b : ((R == S && ph == 0 && j == R) ? a_sp : a);
-        s = __fadd_rn(s, __fmul_rn(k[R + j], __fadd_rn(up, dn)));
-    }
+    for (int j = 1; j <= R; ++j) s = __fadd_rn(s, __fmul_rn(k[R + j], __fadd_rn(win_src<S>(v, ph + j), win_src<S>(v, ph - j))));
     return s;
 }
 
 template <int S, int R>
-__device__ __forceinline__ void col_all(const float *__restrict__ k, float a, float b, float c, float a_sp, float c_sp, float (&s)[S])
+__device__ __forceinline__ void col_all(const float *__restrict__ k, const Win9 &v, float (&s)[S])
 {
 #pragma unroll
-    for (int ph = 0; ph < S; ++ph) s[ph] = col_phase<S, R>(k, ph, a, b, c, a_sp, c_sp);
+    for (int ph = 0; ph < S; ++ph) s[ph] = col_phase<S, R>(k, ph, v);
 }
 
 #ifndef K2_FAST_MAX_THREADS
@@ -501,10 +540,12 @@ __device__ __forceinline__ void stamp2(const K2Params &p, int slot)
     }
 }
 
-template <int S, int R, bool STORE>
+template <int S, int R, bool STORE, bool BZ>
 __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peaks_fast(const K2Params p)
 {
     extern __shared__ __align__(16) float smem[];
+    constexpr int NB = R > S ? 2 : 1; // neighbour depth: cells a tap can reach on either side
+    static_assert(R <= 2 * S, "Gaussian radius beyond two feature cells");
     const int frame = blockIdx.z, part = blockIdx.y;
     stamp2(p, 0);
     const bool compute = part < OPP_N_PARTS;
@@ -512,8 +553,8 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
     const int h = p.g.h, w = p.g.w, H = S * h;
     const int ja = tx * p.tw, jb = min(ja + p.tw, w);
     const int ia = ty * p.th, ib = min(ia + p.th, h);
-    const int jlo = max(ja - 1, 0), jhi = min(jb + 1, w);
-    const int ilo = max(ia - 2, 0), ihi = min(ib + 2, h);
+    const int jlo = max(ja - NB, 0), jhi = min(jb + NB, w);         // cells of the activity masks and of Rrow
+    const int ilo = max(ia - 1 - NB, 0), ihi = min(ib + 1 + NB, h); // halo row + its own filter neighbours
     const int nr = ihi - ilo, ncol = jhi - jlo;
     const int RW = S * ncol;
     float *L = smem;                          // [nr][w] feature rows
@@ -572,8 +613,8 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
     store_units(st_pro);
 
 
-    // ---- which blocks can hold a peak at all?  A pixel of feature cell (r, c) is filtered from the 3x3
-    // cells around it (R <= S, reflection included).  Every float operation of the filter is monotone
+    // ---- which blocks can hold a peak at all?  A pixel of feature cell (r, c) is filtered from the
+    // (2 NB + 1)^2 cells around it (R <= NB * S, reflection included; cells beyond a zero border only lower it).  Every float operation of the filter is monotone
     // in its inputs and the taps are positive, so if those nine values are all <= t then the smoothed
     // pixel is <= t * (sum of taps, rounded up) < t * (1 + 2^-17).  With t = thresh * (1 - 2^-13) the
     // pixel cannot exceed thresh, cannot be a peak, and cannot outrank a pixel that is one: its block
@@ -591,13 +632,13 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
                 const bool hot = c0 + lane_ < ncol && L[r * w + jlo + c0 + lane_] > t_skip;
                 bits |= (unsigned long long)__ballot_sync(0xffffffffu, hot) << c0;
             }
-            // only decided cells [ja, jb) are ever tested, and their 3x3 neighbourhoods lie inside the
-            // staged cells [jlo, jhi) and the staged rows (or end at the image border)
+            // only decided cells [ja, jb) are ever tested, and their neighbourhoods lie inside the
+            // cells [jlo, jhi) and the staged rows (or end at the image border)
             if (lane_ == 0) s_act[r] = bits;
         }
         __syncthreads();
-        // (2) active blocks: warp g owns column group g; lane = feature row; the 3x3 dilation of the bit rows
-        //     is done on the fly (rows r-1, r, r+1 OR-ed, then shifted left and right by one cell)
+        // (2) active blocks: warp g owns column group g; lane = feature row; the dilation of the bit rows
+        //     is done on the fly (rows r-NB .. r+NB OR-ed, then shifted left and right by up to NB cells)
         if (warp_ < ngroups) {
             const int g = warp_;
             const int xa = X0 + 62 * g, xb = min(xa + 62, X1) - 1;
@@ -612,17 +653,22 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
                     v = s_act[r];
                     if (r > 0) v |= s_act[r - 1];
                     if (r + 1 < nr) v |= s_act[r + 1];
-                    v |= (v << 1) | (v >> 1);
+                    if (NB > 1) {
+                        if (r > 1) v |= s_act[r - 2];
+                        if (r + 2 < nr) v |= s_act[r + 2];
+                    }
+                    v |= (v << 1) | (v >> 1) | (NB > 1 ? (v << 2) | (v >> 2) : 0ull);
                 }
                 blk |= (unsigned long long)__ballot_sync(0xffffffffu, (v & dec) != 0) << (32 * k);
             }
             if (lane_ == 0) s_blk[g] = blk;
         }
         __syncthreads();
-        // (3) the cells the row pass must produce: every cell a live block reads (its 64 columns, rows r-1..r+1)
+        // (3) the cells the row pass must produce: every cell a live block reads (its 64 columns, rows r-NB..r+NB)
         for (int r = threadIdx.x; r < nr; r += blockDim.x) {
             unsigned long long need = 0ull;
-            const unsigned long long near3 = (r > 0 ? 7ull << (r - 1) : 3ull); // rows r-1, r, r+1
+            const unsigned long long span = (1ull << (2 * NB + 1)) - 1;
+            const unsigned long long near3 = r >= NB ? span << (r - NB) : span >> (NB - r); // rows r-NB .. r+NB
             for (int g = 0; g < ngroups; ++g) {
                 if (s_blk[g] & near3) {
                     const int xa = X0 + 62 * g, xb = min(xa + 62, X1) - 1;
@@ -643,12 +689,10 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
             const int r = it / ncol, c = jlo + (it - r * ncol);
             if (!((s_need[r] >> (c - jlo)) & 1ull)) continue; // no active block reads this cell
             const float *Lr = L + r * w;
-            const float b = Lr[c];
-            const float a_raw = Lr[max(c - 1, 0)], c_raw = Lr[min(c + 1, w - 1)];
-            const float a = c > 0 ? a_raw : b, cc = c < w - 1 ? c_raw : b;
-            const float a_sp = c > 0 ? a_raw : c_raw, c_sp = c < w - 1 ? c_raw : a_raw;
+            const Win9 win = make_win<NB, BZ>(NB > 1 ? Lr[max(c - 2, 0)] : 0.f, Lr[max(c - 1, 0)], Lr[c], Lr[min(c + 1, w - 1)],
+                                              NB > 1 ? Lr[min(c + 2, w - 1)] : 0.f, c, w);
             float out[S];
-            row_taps<S, R>(p.taps, a, b, cc, a_sp, c_sp, out);
+            row_taps<S, R, BZ>(p.taps, win, out);
             float *d = Rrow + r * RW + S * (c - jlo);
             if (S % 4 == 0) {
 #pragma unroll
@@ -709,10 +753,29 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
         auto ld0 = [&](int i) { return have0 ? col0[(i - ilo) * RW] : NINF; };
         auto ld1 = [&](int i) { return have1 ? col1[(i - ilo) * RW] : NINF; };
 
+        // window of the two columns: rows i-NB .. i+NB of the row-pass result (w?[NB] = row i).  Rows outside the
+        // image hold 0 and are never selected under REFLECT_101 (make_win) / stand as 0 under a zero border.
+        constexpr int NW = 2 * NB + 1;
+        float w0[NW], w1[NW];
+        auto ldr0 = [&](int i) { return (i >= 0 && i < h) ? ld0(i) : 0.f; };
+        auto ldr1 = [&](int i) { return (i >= 0 && i < h) ? ld1(i) : 0.f; };
+        auto load_window = [&](int i) { // all rows but the last (i + NB), which every use fetches itself
+#pragma unroll
+            for (int d = 0; d < NW - 1; ++d) w0[d] = ldr0(i - NB + d), w1[d] = ldr1(i - NB + d);
+        };
+        auto shift_window = [&]() {
+#pragma unroll
+            for (int d = 0; d < NW - 1; ++d) w0[d] = w0[d + 1], w1[d] = w1[d + 1];
+        };
+        auto smooth_rows = [&](int i, float (&s0)[S], float (&s1)[S]) { // the S image rows of feature row i, both columns
+            w0[NW - 1] = ldr0(i + NB), w1[NW - 1] = ldr1(i + NB);
+            const Win9 v0 = make_win<NB, BZ>(w0[0], w0[NB - 1], w0[NB], w0[NB + 1], w0[NW - 1], i, h);
+            const Win9 v1 = make_win<NB, BZ>(w1[0], w1[NB - 1], w1[NB], w1[NB + 1], w1[NW - 1], i, h);
+            col_all<S, R>(p.taps, v0, s0);
+            col_all<S, R>(p.taps, v1, s1);
+        };
         const int i_first = ia > 0 ? ia - 1 : ia;
-        float a0 = 0.f, a1 = 0.f, b0, b1, c0, c1; // rows i-1, i, i+1 of the two columns
-        if (i_first > 0) a0 = ld0(i_first - 1), a1 = ld1(i_first - 1);
-        b0 = ld0(i_first), b1 = ld1(i_first);
+        load_window(i_first);
         float s0[S], s1[S];
         const unsigned long long blk = s_blk[warp]; // bit r: block (this column group, feature row ilo + r) is active
         // the mask is the same in every lane; the vote makes that visible to the compiler (uniform branch,
@@ -725,21 +788,20 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
             n0.pp_h = n0.p_h = n0.p_s = NINF, n1.pp_h = n1.p_h = n1.p_s = NINF;
             open = false;
         };
+        bool stale = false; // the window does not hold the rows around i
         if (ia > 0) { // halo row above the tile: only its last image row is needed
             const int i = ia - 1;
-            c0 = ld0(i + 1), c1 = ld1(i + 1); // i + 1 = ia <= h - 1
             if (active(i)) {
-                col_all<S, R>(p.taps, i > 0 ? a0 : b0, b0, c0, i > 0 ? a0 : c0, c0, s0);
-                col_all<S, R>(p.taps, i > 0 ? a1 : b1, b1, c1, i > 0 ? a1 : c1, c1, s1);
+                smooth_rows(i, s0, s1);
                 step(s0[S - 1], s1[S - 1], 0, false);
                 n0.p_s = NINF, n1.p_s = NINF; // that row belongs to the tile above
+                shift_window();
+            } else {
+                stale = true;
             }
-            a0 = b0, b0 = c0, a1 = b1, b1 = c1;
         }
         // Most feature rows of a column group are inactive on real maps (17 % active on the bench's): a run of them is
-        // stepped over in one go - no loads, no per-row test - and the three-row window (a, b, c) is re-read at the
-        // next active row.
-        bool stale = false; // (a, b) do not hold rows (i - 1, i)
+        // stepped over in one go - no loads, no per-row test - and the window is re-read at the next active row.
         for (int i = ia; i < ib; ++i) {
             if (!active(i)) {
                 if (open) close_block(S * i);
@@ -755,27 +817,20 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
             }
             if (STORE) store_units(3);
             if (stale) {
-                a0 = i > 0 ? ld0(i - 1) : 0.f, a1 = i > 0 ? ld1(i - 1) : 0.f;
-                b0 = ld0(i), b1 = ld1(i);
+                load_window(i);
                 stale = false;
             }
-            const bool top = i == 0, bot = i == h - 1;
-            c0 = bot ? 0.f : ld0(i + 1), c1 = bot ? 0.f : ld1(i + 1);
-            col_all<S, R>(p.taps, top ? b0 : a0, b0, bot ? b0 : c0, top ? c0 : a0, bot ? a0 : c0, s0);
-            col_all<S, R>(p.taps, top ? b1 : a1, b1, bot ? b1 : c1, top ? c1 : a1, bot ? a1 : c1, s1);
+            smooth_rows(i, s0, s1);
 #pragma unroll
             for (int ph = 0; ph < S; ++ph) step(s0[ph], s1[ph], ph, true);
             flush(S * i);
             open = true;
-            a0 = b0, b0 = c0, a1 = b1, b1 = c1;
+            shift_window();
         }
         if (ib < h && active(ib)) { // halo row below the tile: its first image row closes the last row of the tile
             const int i = ib;
-            if (stale) a0 = ld0(i - 1), a1 = ld1(i - 1), b0 = ld0(i), b1 = ld1(i); // ib >= 1
-            const bool bot = i == h - 1;
-            c0 = bot ? 0.f : ld0(i + 1), c1 = bot ? 0.f : ld1(i + 1);
-            col_all<S, R>(p.taps, a0, b0, bot ? b0 : c0, a0, bot ? a0 : c0, s0);
-            col_all<S, R>(p.taps, a1, b1, bot ? b1 : c1, a1, bot ? a1 : c1, s1);
+            if (stale) load_window(i);
+            smooth_rows(i, s0, s1);
             step(s0[0], s1[0], 0, true);
             flush(S * i);
         } else if (open) { // bottom image edge, or an inactive block below: that row counts as -inf
@@ -1857,36 +1912,42 @@ template <typename P> static cudaError_t launch_ex(void (*kern)(const P), dim3 g
     return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-template <int S, int R, bool STORE>
+template <int S, int R, bool STORE, bool BZ>
 static cudaError_t launch_k2_fast_t(const K2Params &p, int n_frames, size_t smem, cudaStream_t st, bool pdl)
 {
+    constexpr int NB = R > S ? 2 : 1;
     int dyn_limit = 0;
-    BIG_SMEM_LIMIT((k2_peaks_fast<S, R, STORE>), dyn_limit);
+    BIG_SMEM_LIMIT((k2_peaks_fast<S, R, STORE, BZ>), dyn_limit);
     if (smem > (size_t)dyn_limit) return cudaErrorInvalidValue;
     dim3 grid(p.nxs * p.nys, STORE ? OPP_N_HEAT : OPP_N_PARTS, n_frames);
     const int groups = (S * p.tw + 61) / 62;
-    if (groups < 1 || groups > K2_FAST_MAX_WARPS || p.th + 4 > 64 || p.tw + 2 > 64) return cudaErrorInvalidValue; // 64-bit activity masks
+    if (groups < 1 || groups > K2_FAST_MAX_WARPS || p.th + 2 + 2 * NB > 64 || p.tw + 2 * NB > 64) return cudaErrorInvalidValue; // 64-bit activity masks
+    if (p.g.h < NB + 1 || p.g.w < NB + 1) return cudaErrorInvalidValue; // make_win's border operands
     const int threads = 32 * groups;
     if (STORE && 2 * ((S * p.tw) >> 2) > threads) return cudaErrorInvalidValue; // two threads per 16-byte column of the tile
-    return launch_ex(k2_peaks_fast<S, R, STORE>, grid, dim3(threads), smem, st, pdl, p);
+    return launch_ex(k2_peaks_fast<S, R, STORE, BZ>, grid, dim3(threads), smem, st, pdl, p);
 }
 
-template <int S, int R>
+template <int S, int R, bool BZ>
 static cudaError_t launch_k2_fast_sr(const K2Params &p, int n_frames, size_t smem, cudaStream_t st, bool pdl)
 {
-    return p.up_conf ? launch_k2_fast_t<S, R, true>(p, n_frames, smem, st, pdl) : launch_k2_fast_t<S, R, false>(p, n_frames, smem, st, pdl);
+    return p.up_conf ? launch_k2_fast_t<S, R, true, BZ>(p, n_frames, smem, st, pdl) : launch_k2_fast_t<S, R, false, BZ>(p, n_frames, smem, st, pdl);
 }
 
-bool k2_fast_supported(const OppGeom &g)
+bool k2_fast_supported(const OppGeom &g, bool border_zero)
 {
-    // integer scale 8 or 4 on both axes, Gaussian radius within one feature cell
-    return (g.S == 8 || g.S == 4) && g.R <= g.S && g.h >= 2 && g.w >= 2;
+    // integer scale 8 or 4 on both axes, Gaussian radius within two feature cells (R > S needs maps of 3 x 3 cells);
+    // the zero-border form is compiled for the Python graph's own size only (x8, k = 25)
+    if (border_zero) return g.S == 8 && g.R == 12 && g.h >= 3 && g.w >= 3;
+    const int nb = g.R > g.S ? 2 : 1;
+    return (g.S == 8 || g.S == 4) && g.R <= 2 * g.S && g.h >= nb + 1 && g.w >= nb + 1;
 }
 
 size_t k2_fast_smem_bytes(const OppGeom &g, int tw, int th)
 {
-    const int nr = (th + 4 < g.h) ? th + 4 : g.h;
-    const int ncol = (tw + 2 < g.w) ? tw + 2 : g.w;
+    const int nb = g.R > g.S ? 2 : 1;
+    const int nr = (th + 2 + 2 * nb < g.h) ? th + 2 + 2 * nb : g.h;
+    const int ncol = (tw + 2 * nb < g.w) ? tw + 2 * nb : g.w;
     size_t fl = ((size_t)nr * g.w + 3) & ~(size_t)3;
     fl += ((size_t)nr * g.S * ncol + 3) & ~(size_t)3;
     fl += 2 * (size_t)(th < g.h ? th : g.h) * g.w; // PAF feature rows of the fused-store variant
@@ -1899,11 +1960,18 @@ cudaError_t launch_k2_fast(const K2Params &p, int n_frames, cudaStream_t st, boo
     size_t need = smem;
     if ((size_t)OPP_N_PARTS * p.capP * sizeof(int) > need) need = (size_t)OPP_N_PARTS * p.capP * sizeof(int);
     if (need > (size_t)g_max_smem) return cudaErrorInvalidValue;
+    if (p.border_zero) { // the Python graph: 'SAME' zero padding, fixed k = 25 (post_process.py:13-32)
+        if (p.g.S == 8 && p.g.R == 12) return launch_k2_fast_sr<8, 12, true>(p, n_frames, need, st, pdl);
+        return cudaErrorInvalidValue;
+    }
 #define K2_CASE(S_, R_)                                                       \
-    if (p.g.S == S_ && p.g.R == R_) return launch_k2_fast_sr<S_, R_>(p, n_frames, need, st, pdl);
+    if (p.g.S == S_ && p.g.R == R_) return launch_k2_fast_sr<S_, R_, false>(p, n_frames, need, st, pdl);
     K2_CASE(8, 8) K2_CASE(8, 6) K2_CASE(8, 4)               // k = 17, 13, 9: the kernel sizes the reference's demos and scripts use
     K2_CASE(8, 7) K2_CASE(8, 5) K2_CASE(8, 3) K2_CASE(8, 2) K2_CASE(8, 1) K2_CASE(8, 0)
     K2_CASE(4, 4) K2_CASE(4, 3) K2_CASE(4, 2) K2_CASE(4, 1) K2_CASE(4, 0)
+    K2_CASE(8, 12)                                          // k = 25, the Python graph's size, under cv::GaussianBlur's border
+    K2_CASE(8, 9) K2_CASE(8, 10) K2_CASE(8, 11) K2_CASE(8, 13) K2_CASE(8, 14) K2_CASE(8, 15) K2_CASE(8, 16)
+    K2_CASE(4, 5) K2_CASE(4, 6) K2_CASE(4, 7) K2_CASE(4, 8)
 #undef K2_CASE
     return cudaErrorInvalidValue;
 }

@@ -50,7 +50,7 @@ struct K2Params {
     float taps[OPP_MAX_KSIZE + 1];
     float thresh;
     unsigned long long *times; // optional [ctas][8] %globaltimer phase stamps (debug, single frame), may be null
-    int border_zero;   // generic kernel: taps outside the image read 0 (Python-path variant) instead of REFLECT_101
+    int border_zero;   // taps outside the image read 0 (Python-path variant) instead of REFLECT_101
     float skip_thresh; // blocks whose 3x3 feature neighbourhood stays <= this cannot hold a peak; -inf disables the skip
 };
 
@@ -102,7 +102,7 @@ struct K1Params {
 };
 
 size_t k2_fast_smem_bytes(const OppGeom &g, int tw, int th);
-bool k2_fast_supported(const OppGeom &g);
+bool k2_fast_supported(const OppGeom &g, bool border_zero);
 cudaError_t launch_k2_fast(const K2Params &p, int n_frames, cudaStream_t st, bool pdl = false);
 cudaError_t launch_k2_generic(const K2Params &p, int n_frames, cudaStream_t st);
 cudaError_t launch_k2_generic_rep(const K2Params &p, int n_frames, cudaStream_t st); // integer scale: reads the feature maps

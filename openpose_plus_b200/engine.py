@@ -178,6 +178,10 @@ class Engine:
     def last_batch_ms(self, ticket):
         return float(self.L.opp_last_batch_ms(self.h, ticket))
 
+    def peak_kernel(self):
+        """'fast' | 'generic_rep' | 'generic': the peak kernel opp_create selected (opp_peak_kernel)."""
+        return self.L.opp_peak_kernel(self.h).decode()
+
     def launch_count(self):
         return int(self.L.opp_launch_count(self.h))
 

@@ -3,8 +3,9 @@ oracle's cv::GaussianBlur restatement on the replicated image.
 
 At an integer scale S the up-sampled map is S x S blocks of one feature value.  For a Gaussian radius R <= S the fast
 kernel therefore (1) runs the row pass on FEATURE rows only, each output pixel seeing at most three distinct neighbours
-(a, b, c) - plus, when R == S, one tap that BORDER_REFLECT_101 sends to the other neighbour at the image edge (a_sp /
-c_sp) - and (2) runs the column pass per feature row with the same three-neighbour structure.  Every product and sum is
+(a, b, c) - five (a2, a, b, c, c2) for S < R <= 2S - plus the single taps at distance exactly S and 2S that
+BORDER_REFLECT_101 sends to another neighbour at the image edge (the *s operands) - and (2) runs the column pass per
+feature row with the same neighbour structure.  Every product and sum is
 the IEEE operation cv::GaussianBlur performs on the same operands in the same order, so the result must be bit-identical
 to blurring the materialised image.  This test restates that decomposition in numpy float32 and checks exactly that, for
 both scales the kernel is compiled for and every radius, including the symmetric-small row forms (k = 3, 5)."""
@@ -16,18 +17,47 @@ from oracle.oracle import Oracle
 f32 = np.float32
 
 
-def row_taps(k, S, R, a, b, c, a_sp, c_sp):
-    def src(o):
-        if o < 0:
-            return a_sp if (R == S and o == -S) else a
-        if o < S:
-            return b
-        return c_sp if (R == S and o == 2 * S - 1) else c
+def make_win(m2, m1, z, p1, p2, i, n, zero):
+    """The nine operands (a2s, a2, as, a, b, c, cs, c2, c2s) the kernel's make_win builds for cell i of n: the cell, its
+    two neighbours on either side, and the values the border rule substitutes for the single taps at distance exactly S
+    and 2S (the *s operands)."""
+    z0 = f32(0)
+    if zero:
+        a = m1 if i > 0 else z0
+        a2 = m2 if i > 1 else z0
+        c = p1 if i < n - 1 else z0
+        c2 = p2 if i < n - 2 else z0
+        return (a2, a2, a, a, z, c, c, c2, c2)
+    a = m1 if i > 0 else z
+    a_s = m1 if i > 0 else p1
+    a2 = m2 if i > 1 else (m1 if i == 1 else p1)
+    a2s = m2 if i > 1 else (z if i == 1 else p2)
+    c = p1 if i < n - 1 else z
+    c_s = p1 if i < n - 1 else m1
+    c2 = p2 if i < n - 2 else (p1 if i == n - 2 else m1)
+    c2s = p2 if i < n - 2 else (z if i == n - 2 else m2)
+    return (a2s, a2, a_s, a, z, c, c_s, c2, c2s)
+
+
+def win_src(win, S, o):
+    """value of the replicated line at offset o from the start of the cell (o in [-2S, 3S-1])"""
+    a2s, a2, a_s, a, b, c, c_s, c2, c2s = win
+    if 0 <= o < S:
+        return b
+    if o < 0:
+        d = -o
+        return a if d < S else a_s if d == S else a2 if d < 2 * S else a2s
+    d = o - S + 1
+    return c if d < S else c_s if d == S else c2 if d < 2 * S else c2s
+
+
+def row_taps(k, S, R, win, small=True):
+    src = lambda o: win_src(win, S, o)  # noqa: E731
     out = []
     for q in range(S):
-        if R == 1:
+        if R == 1 and small:
             s = f32(f32(src(q) * k[1]) + f32(f32(src(q - 1) + src(q + 1)) * k[2]))
-        elif R == 2:
+        elif R == 2 and small:
             s = f32(f32(src(q) * k[2]) + f32(f32(src(q - 1) + src(q + 1)) * k[3]))
             s = f32(s + f32(f32(src(q - 2) + src(q + 2)) * k[4]))
         else:
@@ -39,49 +69,59 @@ def row_taps(k, S, R, a, b, c, a_sp, c_sp):
     return out
 
 
-def col_phase(k, S, R, ph, a, b, c, a_sp, c_sp):
-    s = f32(k[R] * b)
+def col_phase(k, S, R, ph, win):
+    s = f32(k[R] * win[4])
     for j in range(1, R + 1):
-        up = b if ph + j < S else (c_sp if (R == S and ph == S - 1 and j == R) else c)
-        dn = b if ph - j >= 0 else (a_sp if (R == S and ph == 0 and j == R) else a)
-        s = f32(s + f32(k[R + j] * f32(up + dn)))
+        s = f32(s + f32(k[R + j] * f32(win_src(win, S, ph + j) + win_src(win, S, ph - j))))
     return s
 
 
-def fast_model(F, S, ksize):
+def fast_model(F, S, ksize, zero=False, taps=None):
     h, w = F.shape
     R = ksize // 2
-    k = Oracle.gauss_kernel(ksize) if ksize > 1 else np.ones(1, np.float32)
+    k = taps if taps is not None else (Oracle.gauss_kernel(ksize) if ksize > 1 else np.ones(1, np.float32))
+    at = lambda A, r, c: A[min(max(r, 0), A.shape[0] - 1), min(max(c, 0), A.shape[1] - 1)]  # noqa: E731  (clamped: the value is unused when out of range)
     rrow = np.zeros((h, S * w), np.float32)  # row pass, one row per FEATURE row
     for r in range(h):
         for c in range(w):
-            b = F[r, c]
-            a_raw, c_raw = F[r, max(c - 1, 0)], F[r, min(c + 1, w - 1)]
-            a, cc = (a_raw if c > 0 else b), (c_raw if c < w - 1 else b)
-            a_sp, c_sp = (a_raw if c > 0 else c_raw), (c_raw if c < w - 1 else a_raw)
-            rrow[r, S * c:S * c + S] = [b] * S if ksize == 1 else row_taps(k, S, R, a, b, cc, a_sp, c_sp)
+            win = make_win(at(F, r, c - 2), at(F, r, c - 1), F[r, c], at(F, r, c + 1), at(F, r, c + 2), c, w, zero)
+            rrow[r, S * c:S * c + S] = [F[r, c]] * S if ksize == 1 else row_taps(k, S, R, win, small=not zero)
     out = np.zeros((S * h, S * w), np.float32)
     for i in range(h):
-        top, bot = i == 0, i == h - 1
         for x in range(S * w):
-            b = rrow[i, x]
-            a = rrow[i - 1, x] if i > 0 else f32(0)
-            c = rrow[i + 1, x] if i < h - 1 else f32(0)
+            win = make_win(at(rrow, i - 2, x), at(rrow, i - 1, x), rrow[i, x], at(rrow, i + 1, x), at(rrow, i + 2, x), i, h, zero)
             for ph in range(S):
-                out[S * i + ph, x] = b if ksize == 1 else col_phase(k, S, R, ph, b if top else a, b, b if bot else c, c if top else a, a if bot else c)
+                out[S * i + ph, x] = rrow[i, x] if ksize == 1 else col_phase(k, S, R, ph, win)
     return out
 
 
-@pytest.mark.parametrize("S,ksizes", [(8, (1, 3, 5, 7, 9, 11, 13, 15, 17)), (4, (1, 3, 5, 7, 9))])
+@pytest.mark.parametrize("S,ksizes", [(8, (1, 3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 23, 25, 27, 29, 31, 33)), (4, (1, 3, 5, 7, 9, 11, 13, 15, 17))])
 def test_feature_level_arithmetic_equals_blurring_the_replicated_image(S, ksizes):
+    """R <= S: three distinct neighbours; S < R <= 2S (k = 19..33 at x8, the Python graph's 25 included): five."""
     rng = np.random.default_rng(S)
     for ksize in ksizes:
-        for (h, w) in ((5, 6), (2, 7), (3, 2)):
+        for (h, w) in ((5, 6), (2, 7), (3, 2), (3, 3), (4, 9)):
+            if ksize // 2 > S and min(h, w) < 3:
+                continue  # the kernel takes R > S only for maps of at least 3 x 3 cells
             F = rng.random((h, w), dtype=np.float32)
             img = np.repeat(np.repeat(F, S, 0), S, 1)
             want = Oracle.gauss_blur(img, ksize)
             got = fast_model(F, S, ksize)
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (S, ksize, h, w)
+
+
+@pytest.mark.parametrize("S,ksize", [(8, 25), (8, 17), (8, 33), (4, 13), (4, 5), (8, 3)])
+def test_feature_level_arithmetic_with_zero_border(S, ksize):
+    """The Python graph's 'SAME' zero padding (post_process.py:25-26) through the same operand scheme: cells beyond the
+    border stand as 0 and every tap runs the general left-to-right row form."""
+    rng = np.random.default_rng(100 + ksize)
+    taps = Oracle.cdf_kernel(ksize)
+    for (h, w) in ((5, 6), (3, 3), (4, 9)):
+        F = rng.random((h, w), dtype=np.float32)
+        img = np.repeat(np.repeat(F, S, 0), S, 1)
+        want = Oracle.smooth_zero_pad(img, taps)
+        got = fast_model(F, S, ksize, zero=True, taps=taps)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (S, ksize, h, w)
 
 
 def reflect101(p, n):

@@ -55,7 +55,7 @@ def test_generic_kernel_sizes_and_scales(mods):
     conf, paf = synth.render_batch(2, n_people=6, seed0=400)
     # small kernels on x8-replicated maps are all plateaus (thousands of tied peaks), so k = 1, 3, 5
     # (OpenCV's copy / symmetric-small row forms) are exercised at scale 1 and 2 instead
-    for (oh, ow, k) in [(368, 432, 25), (368, 432, 31), (46, 54, 1), (46, 54, 3), (92, 108, 5), (46, 108, 7), (300, 400, 17),
+    for (oh, ow, k) in [(368, 432, 35), (368, 432, 41), (46 * 4, 54 * 4, 19), (46, 54, 1), (46, 54, 3), (92, 108, 5), (46, 108, 7), (300, 400, 17),
                         (369, 433, 9), (46 * 3, 54 * 3, 7), (46 * 4, 54 * 4, 9), (368, 432 * 2, 17)]:
         eng, orc = Engine(46, 54, oh, ow, gauss_kernel_size=k, max_batch=2, max_peaks_per_part=512), Oracle(46, 54, oh, ow, k)
         H.run_and_check(eng, orc, conf, paf, "generic %dx%d k=%d" % (oh, ow, k))
@@ -95,6 +95,61 @@ def test_fast_path_all_kernel_sizes_and_scale_4(mods):
         orc = Oracle(46, 54, oh, ow, k)
         H.run_and_check(eng, orc, conf, paf, "fast x%d k=%d" % (scale, k))
         eng.close()
+
+
+def test_fast_path_wide_kernels(mods):
+    """S < R <= 2S: five neighbour cells instead of three (k = 19..33 at x8 - the Python graph's 25 among them - and
+    k = 11..17 at x4), on rendered frames and on tiny noisy maps where every pixel is within reach of a border (the
+    REFLECT_101 operands at distance exactly S and 2S), single- and multi-tile."""
+    Engine, Oracle, H = mods
+    conf, paf = synth.render_batch(3, n_people=6, seed0=900)
+    for (scale, k) in [(8, 19), (8, 21), (8, 23), (8, 25), (8, 27), (8, 29), (8, 31), (8, 33), (4, 11), (4, 13), (4, 15), (4, 17)]:
+        oh, ow = 46 * scale, 54 * scale
+        eng, orc = Engine(46, 54, oh, ow, gauss_kernel_size=k, max_batch=3, max_peaks_per_part=512), Oracle(46, 54, oh, ow, k)
+        assert eng.peak_kernel() == "fast", (scale, k)
+        H.run_and_check(eng, orc, conf, paf, "wide x%d k=%d" % (scale, k))
+        eng.close()
+    rng = np.random.default_rng(12)
+    for (fh, fw, scale, k) in [(3, 3, 8, 33), (3, 3, 8, 25), (3, 7, 8, 25), (5, 4, 8, 19), (4, 3, 8, 31), (9, 31, 8, 25), (33, 4, 8, 33),
+                               (3, 3, 4, 17), (6, 5, 4, 11), (13, 17, 4, 13), (60, 70, 8, 25), (20, 120, 8, 27), (64, 61, 8, 25)]:
+        n = 3
+        conf = (rng.random((n, 19, fh, fw), dtype=np.float32) ** (3 if fh * fw < 1000 else 12)).astype(np.float32)  # large maps: sparser, within the capacities
+        paf = (rng.random((n, 38, fh, fw), dtype=np.float32) * 2 - 1).astype(np.float32)
+        conf[1] *= 0.04
+        eng = Engine(fh, fw, fh * scale, fw * scale, gauss_kernel_size=k, max_batch=n, max_peaks_per_part=1024, max_cands_per_limb=65536, max_humans=2048)
+        orc = Oracle(fh, fw, fh * scale, fw * scale, k)
+        assert eng.peak_kernel() == "fast", (fh, fw, scale, k)
+        H.run_and_check(eng, orc, conf, paf, "wide %dx%d x%d k=%d" % (fh, fw, scale, k))
+        eng.close()
+    # maps of two cells along an axis cannot hold the five-cell window: the replication-aware generic kernel takes them
+    eng = Engine(2, 5, 16, 40, gauss_kernel_size=25, max_batch=1)
+    assert eng.peak_kernel() == "generic_rep"
+    eng.close()
+
+
+def test_wide_kernels_fast_and_generic_agree(mods, monkeypatch):
+    """k = 25 under both border rules through the fast kernel and, with OPP_FORCE_GENERIC=1, through the
+    replication-aware generic kernel it replaced: both bit-exact against the oracle, hence against each other.  Noisy
+    maps reaching into every border (where the two border rules differ)."""
+    Engine, Oracle, H = mods
+    from openpose_plus_b200 import _capi as capi
+    rng = np.random.default_rng(13)
+    conf, paf = synth.render_batch(3, n_people=8, seed0=910)
+    conf[:, :18] = np.maximum(conf[:, :18], (0.4 * rng.random((3, 18, 46, 54), dtype=np.float32) ** 4).astype(np.float32))
+    for variant in (capi.VARIANT_CPP, capi.VARIANT_PYTHON):
+        orc = Oracle(46, 54, 368, 432, 25, variant=variant)
+        for force in ("0", "1"):
+            monkeypatch.setenv("OPP_FORCE_GENERIC", force)
+            eng = Engine(46, 54, gauss_kernel_size=25, max_batch=3, max_peaks_per_part=512, max_cands_per_limb=8192, max_humans=512, variant=variant)
+            assert eng.peak_kernel() == ("generic_rep" if force == "1" else "fast")
+            H.run_and_check(eng, orc, conf, paf, "k=25 variant %d force_generic=%s" % (variant, force))
+            if force == "0":  # and with the up-sampled maps materialised by the same kernel (the fused store path)
+                import torch
+                cu, pu = torch.empty((3, 19, 368, 432), device="cuda"), torch.empty((3, 38, 368, 432), device="cuda")
+                H.run_and_check(eng, orc, conf, paf, "k=25 variant %d, fused store" % variant, conf_up=cu, paf_up=pu)
+                o = orc.run(conf[2], paf[2], maps=True)
+                assert np.array_equal(cu[2].cpu().numpy(), o["conf_up"]) and np.array_equal(pu[2].cpu().numpy(), o["paf_up"])
+            eng.close()
 
 
 def test_small_and_odd_geometries_on_the_fast_path(mods):
