@@ -212,31 +212,54 @@ void plan_k3_smem(opp_handle_s *h)
     const size_t cand_bytes = 2 * (size_t)capC * 12;
     p.cand_in_smem = (fixed + cand_bytes) <= budget / 2;
     p.paf_in_smem = (fixed + (p.cand_in_smem ? cand_bytes : 0) + paf_bytes) <= (size_t)(budget * 0.45);
+    // The PAF tile is dead once the limb's pairs are scored and the second candidate buffer (the sort's output) is
+    // not written before that: the two share their bytes.
     p.off_paf = (int)off;
-    if (p.paf_in_smem) off += align_up(paf_bytes, 16);
+    { // cand0 [capC], cand1 [capC]: cand1 starts where the PAF tile starts when both are in shared memory
+        const size_t c0 = p.cand_in_smem ? align_up((size_t)capC * 12, 16) : 0, c1 = c0;
+        const size_t tile = p.paf_in_smem ? align_up(paf_bytes, 16) : 0;
+        p.off_cand1 = (int)off;                      // cand1 first (aliases the tile) ...
+        off += c1 > tile ? c1 : tile;
+        p.off_cand = (int)off, off += c0;            // ... then cand0, which scoring fills while the tile is read
+    }
     p.off_pk = (int)off, off += 2 * (size_t)capP * sizeof(int2);
-    p.off_cand = (int)off;
-    if (p.cand_in_smem) off += align_up(cand_bytes, 16);
     p.off_used = (int)off, off += align_up(2 * (size_t)capP, 16);
     p.off_misc = (int)off, off += 64;
     p.off_keys = (int)off, off += align_up(2 * (size_t)capP * sizeof(int), 16); // unordered keys of the limb's two parts
+    // survivors of the quick PAF test, later the matching's per-candidate state (one byte each): at least two rounds of
+    // the CTA's threads, and room for capC state bytes where that is affordable
+    size_t surv_ints = 1024;
+    if (p.cand_in_smem && (size_t)capC > surv_ints * 4) surv_ints = ((size_t)capC + 3) / 4;
+    p.off_surv = (int)off, p.surv_cap = (int)surv_ints, off += align_up(surv_ints * sizeof(int), 16);
     const size_t phase1 = off;
     // assembly phase (re-uses the same bytes): partial humans, survivors, connections, peak x/y/score
     off = 0;
     p.off_href = 0, off += align_up((size_t)capH * 21 * sizeof(int), 16);
     p.off_keep = (int)off, off += align_up((size_t)capH * sizeof(int), 16);
-    const size_t conn_all = (size_t)OPP_N_PAIRS * capP * sizeof(opp_conn_t), conn_one = (size_t)capP * sizeof(opp_conn_t);
-    const size_t pk_bytes = (size_t)OPP_N_PARTS * capP * sizeof(int2); // x | y << 16, score
+    // Staging areas are sized for crowded REAL frames (40 people: ~800 peaks, ~850 connections), not for the capacities'
+    // worst case (19 x capP connections): a frame beyond them takes the limb-by-limb / global-memory forms of the same
+    // code (decided per frame in assemble_frame).  The footprint of every limb CTA is what limits CTAs per SM.
+    const size_t conn_cap = std::max<size_t>(capP, std::min<size_t>((size_t)OPP_N_PAIRS * capP, 1024));
+    const size_t pk_cap = std::min<size_t>((size_t)OPP_N_PARTS * capP, 1024);
+    const size_t conn_all = conn_cap * sizeof(opp_conn_t), conn_one = (size_t)capP * sizeof(opp_conn_t);
+    const size_t pk_bytes = pk_cap * sizeof(int2); // x | y << 16, score
     p.conns_in_smem = off + conn_all + pk_bytes <= (size_t)(budget * 0.45);
+    p.conn_cap = p.conns_in_smem ? (int)conn_cap : capP;
     p.off_conn = (int)off, off += align_up(p.conns_in_smem ? conn_all : conn_one, 16);
     p.score_in_smem = off + pk_bytes <= budget / 2;
+    p.pk_cap = p.score_in_smem ? (int)pk_cap : 0;
     p.off_score = (int)off;
     if (p.score_in_smem) off += pk_bytes;
-    const size_t owner_bytes = (size_t)OPP_N_PARTS * capP * sizeof(int);
+    // forest tables: s_c1 [17][capP] u16, s_in bitmap over 18 capP peak ids, s_lmb [conn_cap] u8
+    const size_t owner_bytes = align_up((size_t)17 * capP * 2, 16) + align_up(((size_t)OPP_N_PARTS * capP + 31) / 32 * 4, 16) + align_up(conn_cap, 16);
     p.owner_in_smem = p.conns_in_smem && p.score_in_smem && off + owner_bytes <= budget / 2;
     p.off_owner = (int)off;
     if (p.owner_in_smem) off += owner_bytes;
     h->k3_smem = phase1 > off ? phase1 : off;
+    if (const char *e = getenv("OPP_K3_SMEM_MIN")) { // experiments: pad the footprint (fewer CTAs per SM)
+        const size_t m = (size_t)atoi(e);
+        if (m > h->k3_smem && m <= budget) h->k3_smem = m;
+    }
 }
 
 int free_slot(opp_handle_s *h, Slot &s)
@@ -956,6 +979,14 @@ int opp_wait(opp_handle_t h, int ticket)
         const bool up = s.batch.conf_up || s.batch.paf_up;
         for (int i = 0; i < 6; ++i)
             if (i >= 2 || up) cudaEventElapsedTime(&t[i], h->trace_base, s.tr[i]);
+        if (const char *dump = s.d_times ? getenv("OPP_TRACE_DUMP") : nullptr) { // raw stamps of every (frame, limb) of the batch
+            std::vector<unsigned long long> all((size_t)s.n_frames * OPP_N_PAIRS * 12);
+            cudaMemcpy(all.data(), s.d_times, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            if (FILE *f = fopen(dump, "wb")) {
+                fwrite(all.data(), sizeof(unsigned long long), all.size(), f);
+                fclose(f);
+            }
+        }
         if (s.d_times && s.n_frames == 1) { // phase stamps of the limb kernel, relative to the earliest CTA start
             unsigned long long t[OPP_N_PAIRS * 12];
             cudaMemcpy(t, s.d_times, sizeof t, cudaMemcpyDeviceToHost);

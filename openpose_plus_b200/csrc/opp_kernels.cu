@@ -1047,6 +1047,65 @@ struct Cand {
     float s;
 };
 
+// PAF line integral of one (a, b) peak pair: src/paf.cpp:86-127 with get_paf_vectors :313-335.  QUICK evaluates
+// only the four middle samples (i = 3..6) and answers "can this pair still be accepted?": acceptance needs more
+// than 8 of the 10 samples above THRESH_VECTOR_SCORE (:119-121), so two failures among ANY samples rule the pair
+// out - exactly, whatever the others say.  Most pairs of a frame join peaks of different people, whose segment
+// crosses empty PAF in the middle: they leave after 4 samples instead of 10 and the survivors (re-evaluated in
+// full, same operations in the same order) fill whole warps.
+struct PairCtx {
+    const float *px, *py; // the limb's x / y PAF planes (feature resolution)
+    const OppGeom *g;
+    int w, H, sshift;
+    float thr;
+};
+
+template <bool QUICK>
+__device__ __forceinline__ bool score_pair(const PairCtx &c, const int2 A, const int2 B, float &crit2)
+{
+    const int dx = B.x - A.x, dy = B.y - A.y;
+    // norm = (float)sqrt((double)l2)  (src/paf.cpp:91).  Rounding sqrt to 53 and then to 24 bits equals
+    // rounding it to 24 bits directly (double rounding is innocuous for sqrt when 53 >= 2*24 + 2),
+    // so the single-precision IEEE sqrt gives the same float whenever l2 is exact in float.
+    const int l2 = dx * dx + dy * dy;
+    if (l2 == 0) return false; // `norm < 1e-12` is true only for coincident peaks
+    const float norm = l2 < (1 << 24) ? __fsqrt_rn((float)l2) : (float)sqrt((double)l2);
+    const float vx = __fdiv_rn((float)dx, norm), vy = __fdiv_rn((float)dy, norm);
+    const float step_x = __fdiv_rn((float)dx, 10.f), step_y = __fdiv_rn((float)dy, 10.f); // :321-322
+    float scores = 0.f;
+    int cnt = 0;
+#pragma unroll
+    for (int i = QUICK ? 3 : 0; i < (QUICK ? 7 : 10); ++i) {
+        // roundpaf(peak1.x + i * STEP_X): float mul, float add, double +0.5, truncate  :325-326,337
+        const float fx = __fadd_rn((float)A.x, __fmul_rn((float)i, step_x));
+        const float fy = __fadd_rn((float)A.y, __fmul_rn((float)i, step_y));
+        // No clamp (the reference has none): |i * STEP| <= 0.9 |d| (1 + 2^-22) and |d| >= 1 on a moving axis, so every
+        // sample rounds to a pixel between the two peaks, which lie inside the image.
+        const int lx = round_paf(fx), ly = round_paf(fy);
+        float vpx, vpy;
+        if (c.sshift >= 0) { // replication by a power of two: one shared index, no integer division
+            const int fi = (ly >> c.sshift) * c.w + (lx >> c.sshift);
+            vpx = c.px[fi], vpy = c.py[fi];
+        } else {
+            vpx = upsample_at(*c.g, c.px, ly, lx);
+            vpy = upsample_at(*c.g, c.py, ly, lx);
+        }
+        const float score = __fadd_rn(__fmul_rn(vx, vpx), __fmul_rn(vy, vpy)); // :108-109
+        scores = __fadd_rn(scores, score);
+        cnt += (score > c.thr);
+    }
+    if (QUICK) return cnt >= 3;
+    // scores / STEP_PAF + std::min(0.0, 0.5 * height / norm - 1.0)   :115-116
+    const float s10 = __fdiv_rn(scores, 10.f);
+    if (norm <= 0.5f * (float)c.H) {
+        crit2 = s10; // 0.5*H/norm >= 1 exactly, so the penalty is min(0.0, >= 0) = 0 and (float)((double)s10 + 0.0) == s10
+    } else {
+        const double pen = __dsub_rn(__ddiv_rn(0.5 * (double)c.H, (double)norm), 1.0);
+        crit2 = (float)__dadd_rn((double)s10, pen < 0.0 ? pen : 0.0);
+    }
+    return cnt > 8 && crit2 > 0.f;
+}
+
 __device__ __forceinline__ bool cand_gt(const Cand &a, const Cand &b) { return a.s > b.s; }
 
 // libstdc++ (GCC 13) std::sort with comp(a,b) = a.score > b.score, as called at src/paf.cpp:151-152.
@@ -1185,6 +1244,100 @@ __device__ void std_sort_desc(Cand *v, int n)
         insertion_sort_range(v, v + n);
 }
 
+// The partition loop of that std::sort (everything before __final_insertion_sort) in parallel, whole CTA, in place.
+// tests/test_sort_model.py is the executable CPU model and carries the argument:
+//   * __unguarded_partition is a Hoare partition: with A = the positions (ascending) whose element does not beat the
+//     pivot and B = the positions (descending) the pivot does not beat, the sequential loop swaps A[k] <-> B[k] for
+//     every k with A[k] < B[k] and returns cut = A[K] if A[K] < B[K-1] else B[K-1] (K swaps; A[0] when K = 0).  A warp
+//     builds both lists with ballots and does the swaps at once;
+//   * the two sides of a cut are independent: the ranges of one level go to different warps;
+//   * a range whose depth budget is spent is heap-sorted sequentially, as libstdc++ does.
+// What remains (__final_insertion_sort) is an insertion sort = the stable order of the array left behind, which the
+// caller produces with a rank sort.  pos_a / pos_b: scratch, n entries each; rng: scratch, 4 (n / 17 + 2) ints.
+__device__ void std_sort_partition_rounds(Cand *v, int n, unsigned short *pos_a, unsigned short *pos_b, int *rng)
+{
+    __shared__ int s_rcnt[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int max_r = n / 17 + 2;
+    int *rng_lo[2] = {rng, rng + 2 * max_r}; // per level: {first | last << 16, depth}
+    if (tid == 0) {
+        int lg = 0;
+        for (int t = n; t > 1; t >>= 1) ++lg;
+        s_rcnt[0] = n > 16 ? 1 : 0, s_rcnt[1] = 0;
+        rng[0] = 0 | (n << 16), rng[1] = 2 * lg;
+    }
+    __syncthreads();
+    for (int cur = 0;; cur ^= 1) {
+        const int ncur = s_rcnt[cur];
+        if (ncur == 0) break;
+        for (int r = warp; r < ncur; r += nwarps) {
+            const int packed = rng_lo[cur][2 * r], depth = rng_lo[cur][2 * r + 1];
+            const int f = packed & 0xffff, l = (packed >> 16) & 0xffff;
+            if (depth == 0) {
+                if (lane == 0) heap_sort_range(v + f, v + l);
+                continue;
+            }
+            if (lane == 0) { // __move_median_to_first(first, first + 1, mid, last - 1)
+                Cand *first = v + f, *a = first + 1, *b = first + (l - f) / 2, *c = v + l - 1;
+                if (cand_gt(*a, *b)) {
+                    if (cand_gt(*b, *c))
+                        cswap(first, b);
+                    else if (cand_gt(*a, *c))
+                        cswap(first, c);
+                    else
+                        cswap(first, a);
+                } else if (cand_gt(*a, *c))
+                    cswap(first, a);
+                else if (cand_gt(*b, *c))
+                    cswap(first, c);
+                else
+                    cswap(first, b);
+            }
+            __syncwarp();
+            const float piv = v[f].s;
+            // both lists in one ascending pass (B is read backwards afterwards)
+            int cnt_a = 0, cnt_b = 0;
+            const unsigned lt = (1u << lane) - 1;
+            for (int base = f + 1; base < l; base += 32) {
+                const int q = base + lane;
+                const bool in = q < l;
+                const float sq = in ? v[q].s : 0.f;
+                const bool fa = in && !(sq > piv), fb = in && !(piv > sq);
+                const unsigned ma = __ballot_sync(0xffffffffu, fa), mb = __ballot_sync(0xffffffffu, fb);
+                if (fa) pos_a[f + cnt_a + __popc(ma & lt)] = (unsigned short)q;
+                if (fb) pos_b[f + cnt_b + __popc(mb & lt)] = (unsigned short)q;
+                cnt_a += __popc(ma), cnt_b += __popc(mb);
+            }
+            __syncwarp();
+            auto A = [&](int k) { return (int)pos_a[f + k]; };
+            auto B = [&](int k) { return (int)pos_b[f + cnt_b - 1 - k]; };
+            const int m = min(cnt_a, cnt_b);
+            int K = 0; // A ascends and B descends: A[k] < B[k] holds for a prefix of k
+            for (int base = 0; base < m; base += 32) {
+                const int k = base + lane;
+                const unsigned mk = __ballot_sync(0xffffffffu, k < m && A(k) < B(k));
+                K += __popc(mk);
+                if (mk != 0xffffffffu) break;
+            }
+            const int cut = K == 0 ? A(0) : ((K < cnt_a && A(K) < B(K - 1)) ? A(K) : B(K - 1));
+            for (int k = lane; k < K; k += 32) cswap(v + A(k), v + B(k));
+            if (lane == 0) {
+                if (l - cut > 16) {
+                    const int i = atomicAdd(&s_rcnt[cur ^ 1], 1);
+                    rng_lo[cur ^ 1][2 * i] = cut | (l << 16), rng_lo[cur ^ 1][2 * i + 1] = depth - 1;
+                }
+                if (cut - f > 16) {
+                    const int i = atomicAdd(&s_rcnt[cur ^ 1], 1);
+                    rng_lo[cur ^ 1][2 * i] = f | (cut << 16), rng_lo[cur ^ 1][2 * i + 1] = depth - 1;
+                }
+            }
+        }
+        __syncthreads(); // this level's swaps and child ranges are complete
+        if (tid == 0) s_rcnt[cur] = 0;
+        __syncthreads();
+    }
+}
+
 __device__ __forceinline__ void stamp(const K3Params &p, int frame, int pair_id, int slot)
 {
     if (p.times && threadIdx.x == 0) {
@@ -1217,7 +1370,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
     const int n_peaks = pofs[OPP_N_PARTS];
     const opp_peak_t *peaks = p.peaks + (size_t)frame * OPP_N_PARTS * capP;
     if (threadIdx.x <= OPP_N_PARTS) p.part_ofs[frame * (OPP_N_PARTS + 1) + threadIdx.x] = pofs[threadIdx.x]; // for opp_debug_fetch
-    const bool all_conns = p.conns_in_smem != 0, pk_smem = p.score_in_smem != 0;
+    const bool pk_smem = p.score_in_smem != 0 && n_peaks <= p.pk_cap;
     if (threadIdx.x < 32) { // connection counts of the 19 limbs and their exclusive prefix sums, one warp scan
         const int ln = threadIdx.x;
         const int nc = ln < OPP_N_PAIRS ? __ldcg(p.n_conns + frame * OPP_N_PAIRS + ln) : 0;
@@ -1236,14 +1389,13 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
     // enters a human as the SECOND part of a tree-limb connection; s_lmb[t] = limb of flattened connection t.
     unsigned short *s_c1 = reinterpret_cast<unsigned short *>(smem_raw + p.off_owner);                                     // [17][capP]
     unsigned *s_in = reinterpret_cast<unsigned *>(smem_raw + p.off_owner + (((size_t)17 * capP * 2 + 15) & ~(size_t)15)); // [ceil(18 capP / 32)]
-    unsigned char *s_lmb = reinterpret_cast<unsigned char *>(s_in + (OPP_N_PARTS * capP + 31) / 32);                       // [19 capP]
+    unsigned char *s_lmb = reinterpret_cast<unsigned char *>(s_in + (((OPP_N_PARTS * capP + 31) / 32 + 3) & ~3));           // [conn_cap]
     __shared__ int s_pofs[OPP_N_PARTS + 1];
     __shared__ int s_nwarp[OPP_THREADS / 32];
     __shared__ unsigned char s_pa[OPP_N_PAIRS], s_pb[OPP_N_PAIRS]; // c_pair_a / c_pair_b for lane-divergent limb indices
     if (threadIdx.x >= 96 && threadIdx.x < 96 + OPP_N_PAIRS) s_pa[threadIdx.x - 96] = (unsigned char)c_pair_a[threadIdx.x - 96], s_pb[threadIdx.x - 96] = (unsigned char)c_pair_b[threadIdx.x - 96];
-    const bool use_owner = p.owner_in_smem != 0 && all_conns;
     if (threadIdx.x >= 64 && threadIdx.x < 64 + OPP_N_PARTS + 1) s_pofs[threadIdx.x - 64] = pofs[threadIdx.x - 64];
-    if (use_owner) {
+    if (p.owner_in_smem) { // cleared before the frame's connection count is known
         for (int t = threadIdx.x; t < 17 * capP; t += blockDim.x) s_c1[t] = 0xffff;
         for (int t = threadIdx.x; t < (OPP_N_PARTS * capP + 31) / 32; t += blockDim.x) s_in[t] = 0u;
         for (int t = threadIdx.x; t < capH * OPP_N_PARTS; t += blockDim.x) hr[(t / OPP_N_PARTS) * HR_WORDS + HR_PART + t % OPP_N_PARTS] = -1;
@@ -1252,6 +1404,9 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
         for (int t = threadIdx.x; t < n_peaks; t += blockDim.x)
             s_pk[t] = make_int2(__ldcg(&peaks[t].x) | (__ldcg(&peaks[t].y) << 16), __float_as_int(__ldcg(&peaks[t].score)));
     __syncthreads();
+    // frames with more connections than the staging area holds are assembled limb by limb (same code, one warp)
+    const bool all_conns = p.conns_in_smem != 0 && s_coff[OPP_N_PAIRS] <= p.conn_cap;
+    const bool use_owner = p.owner_in_smem != 0 && all_conns;
     if (all_conns) { // every connection of the frame in ONE round trip: the warps take the limbs in turn, a lane per connection
         for (int l = threadIdx.x >> 5; l < OPP_N_PAIRS; l += blockDim.x >> 5) {
             const int nc = s_nc[l], base = s_coff[l], pa_ofs = s_pofs[s_pa[l]];
@@ -1340,13 +1495,22 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
                             flags |= OPP_FLAG_UB_ERASE_PAST_END; // libstdc++ 13: nothing moves, size shrinks
                             if (n > 0) --n;
                         } else {
+                            // records e+1 .. n-1 move down one record: 128 words per step (a step's loads end before its
+                            // stores begin, and a later step only loads words no earlier step has stored)
                             const int w0 = e * HR_WORDS, w1 = (n - 1) * HR_WORDS;
-                            for (int wbase = w0; wbase < w1; wbase += 32) {
-                                const int wd = wbase + lane;
-                                int v = 0;
-                                if (wd < w1) v = hr[wd + HR_WORDS];
+                            for (int wbase = w0; wbase < w1; wbase += 128) {
+                                int v[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const int wd = wbase + 32 * u + lane;
+                                    v[u] = wd < w1 ? hr[wd + HR_WORDS] : 0;
+                                }
                                 __syncwarp();
-                                if (wd < w1) hr[wd] = v;
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const int wd = wbase + 32 * u + lane;
+                                    if (wd < w1) hr[wd] = v[u];
+                                }
                                 __syncwarp();
                             }
                             --n;
@@ -1496,7 +1660,10 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
             }
             hq[HR_NPARTS] = np, hq[HR_SCORE] = __float_as_int(sc);
         }
-        flags |= __syncthreads_or(tflags);
+        // the flag BITS of all threads (__syncthreads_or only answers "any non-zero")
+        if (tflags) atomicOr(&s_state[5], tflags);
+        __syncthreads();
+        flags |= s_state[5];
         n = created, hist_max = created;
     };
 
@@ -1615,10 +1782,11 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
         out[o].parts[i] = bp;
         if (i == 0) out[o].score = __int_as_float(hr[q * HR_WORDS + HR_SCORE]);
     }
-    uflags = __syncthreads_or(uflags);
+    if (uflags) atomicOr(&s_state[6], uflags);
+    __syncthreads();
     if (threadIdx.x == 0) {
         p.n_humans[frame] = n_out;
-        const int fl = s_state[2] | uflags;
+        const int fl = s_state[2] | s_state[6];
         const int all = atomicOr(p.flags + frame, fl) | fl; // every other writer of this word finished before this CTA became last
         if (p.flags_out) p.flags_out[frame] = all;
         p.stats[frame * 4 + 0] = s_state[0];
@@ -1699,13 +1867,18 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
     Cand *cand0, *cand1;
     if (p.cand_in_smem) {
         cand0 = reinterpret_cast<Cand *>(smem_raw + p.off_cand);
-        cand1 = cand0 + capC;
+        cand1 = reinterpret_cast<Cand *>(smem_raw + p.off_cand1); // the PAF tile's bytes: written only after the scoring loop
     } else {
         cand0 = reinterpret_cast<Cand *>(p.cand_scratch) + ((size_t)frame * OPP_N_PAIRS + pair_id) * 2 * capC;
         cand1 = cand0 + capC;
     }
 
     stamp(p, frame, pair_id, 0);
+    if (p.times && tid == 0) { // which SM ran this CTA (slot 11)
+        unsigned sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        p.times[((size_t)frame * OPP_N_PAIRS + pair_id) * 12 + 11] = sm + 1;
+    }
     // this limb's two parts: keys -> raster order (all_peaks slices in global memory, (x, y) lists in shared memory)
     {
         PeakSource src;
@@ -1729,78 +1902,74 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
         if (paf_bulk) bulk_wait(&s_mbar, 0);
         stamp(p, frame, pair_id, 1);
 
-        const int H = p.g.H, W = p.g.W;
-        const int sshift = (p.g.S > 0 && (p.g.S & (p.g.S - 1)) == 0) ? 31 - __clz(p.g.S) : -1;
+        PairCtx pc;
+        pc.px = px_plane, pc.py = py_plane, pc.g = &p.g, pc.w = w, pc.H = p.g.H, pc.thr = p.thr_vec;
+        pc.sshift = (p.g.S > 0 && (p.g.S & (p.g.S - 1)) == 0) ? 31 - __clz(p.g.S) : -1;
         int overflow = 0;
-        for (long base = 0; base < n_pairs; base += blockDim.x) {
-            const long idx = base + tid;
-            bool accept = false;
-            float crit2 = 0.f;
-            int ia = 0, ib = 0;
-            if (idx < n_pairs) {
-                ia = (int)(idx / nb), ib = (int)(idx - (long)ia * nb);
-                const int2 A = s_pa[ia], B = s_pb[ib];
-                const int dx = B.x - A.x, dy = B.y - A.y;
-                // norm = (float)sqrt((double)l2)  (src/paf.cpp:91).  Rounding sqrt to 53 and then to 24 bits equals
-                // rounding it to 24 bits directly (double rounding is innocuous for sqrt when 53 >= 2*24 + 2),
-                // so the single-precision IEEE sqrt gives the same float whenever l2 is exact in float.
-                const int l2 = dx * dx + dy * dy;
-                const float norm = l2 < (1 << 24) ? __fsqrt_rn((float)l2) : (float)sqrt((double)l2);
-                if (l2 != 0) { // `norm < 1e-12` is true only for coincident peaks
-                    const float vx = __fdiv_rn((float)dx, norm), vy = __fdiv_rn((float)dy, norm);
-                    const float step_x = __fdiv_rn((float)dx, 10.f), step_y = __fdiv_rn((float)dy, 10.f); // :321-322
-                    float scores = 0.f;
-                    int cnt = 0;
-#pragma unroll
-                    for (int i = 0; i < 10; ++i) {
-                        // roundpaf(peak1.x + i * STEP_X): float mul, float add, double +0.5, truncate  :325-326,337
-                        const float fx = __fadd_rn((float)A.x, __fmul_rn((float)i, step_x));
-                        const float fy = __fadd_rn((float)A.y, __fmul_rn((float)i, step_y));
-                        int lx = round_paf(fx), ly = round_paf(fy);
-                        lx = clip_idx(lx, W), ly = clip_idx(ly, H);
-                        float vpx, vpy;
-                        if (sshift >= 0) { // replication by a power of two: one shared index, no integer division
-                            const int fi = (ly >> sshift) * w + (lx >> sshift);
-                            vpx = px_plane[fi], vpy = py_plane[fi];
-                        } else {
-                            vpx = upsample_at(p.g, px_plane, ly, lx);
-                            vpy = upsample_at(p.g, py_plane, ly, lx);
-                        }
-                        const float score = __fadd_rn(__fmul_rn(vx, vpx), __fmul_rn(vy, vpy)); // :108-109
-                        scores = __fadd_rn(scores, score);
-                        cnt += (score > p.thr_vec);
-                    }
-                    // scores / STEP_PAF + std::min(0.0, 0.5 * height / norm - 1.0)   :115-116
-                    const float s10 = __fdiv_rn(scores, 10.f);
-                    if (norm <= 0.5f * (float)H) {
-                        crit2 = s10; // 0.5*H/norm >= 1 exactly, so the penalty is min(0.0, >= 0) = 0 and (float)((double)s10 + 0.0) == s10
-                    } else {
-                        const double pen = __dsub_rn(__ddiv_rn(0.5 * (double)H, (double)norm), 1.0);
-                        crit2 = (float)__dadd_rn((double)s10, pen < 0.0 ? pen : 0.0);
-                    }
-                    accept = cnt > 8 && crit2 > 0.f;
-                }
-            }
-            // order-preserving append (candidates must stay a-major / b-minor: it is std::sort's input order)
-            const unsigned m = __ballot_sync(0xffffffffu, accept);
+        // ordered block compaction: the threads with `flag` learn their position after the `count` entries already
+        // there, in thread order (candidates must stay a-major / b-minor: it is std::sort's input order)
+        auto place = [&](bool flag, int count, int &pos) -> int {
+            const unsigned m = __ballot_sync(0xffffffffu, flag);
             if (lane == 0) s_misc[warp] = __popc(m);
             __syncthreads();
-            int before = n_cand;
-            for (int q = 0; q < warp; ++q) before += s_misc[q];
-            int total = 0;
-            for (int q = 0; q < nwarps; ++q) total += s_misc[q];
-            if (accept) {
-                const int pos = before + __popc(m & ((1u << lane) - 1));
-                if (pos < capC) {
-                    Cand cd;
-                    cd.i1 = ofs_a + ia, cd.i2 = ofs_b + ib, cd.s = crit2;
-                    cand0[pos] = cd;
-                } else
-                    overflow = 1;
+            int before = count, total = 0;
+            for (int q = 0; q < nwarps; ++q) {
+                const int cq = s_misc[q];
+                if (q < warp) before += cq;
+                total += cq;
             }
-            n_cand += total;
-            __syncthreads();
+            pos = before + __popc(m & ((1u << lane) - 1));
+            return total;
+        };
+        int *s_surv = reinterpret_cast<int *>(smem_raw + p.off_surv); // [surv_cap] pairs that passed the quick test, in order
+        const unsigned n_pairs_u = (unsigned)n_pairs, nb_u = (unsigned)nb;
+        unsigned next = 0;
+        int n_surv_total = 0;
+        while (next < n_pairs_u) {
+            // (1) quick test of the next pairs until the survivor list is (nearly) full
+            int n_surv = 0;
+            while (next < n_pairs_u && n_surv + (int)blockDim.x <= p.surv_cap) {
+                const unsigned idx = next + tid;
+                bool alive = false;
+                if (idx < n_pairs_u) {
+                    const unsigned ia = idx / nb_u, ib = idx - ia * nb_u;
+                    float unused;
+                    alive = score_pair<true>(pc, s_pa[ia], s_pb[ib], unused);
+                }
+                int pos;
+                const int total = place(alive, n_surv, pos);
+                if (alive) s_surv[pos] = (int)idx;
+                n_surv += total;
+                next += blockDim.x;
+                __syncthreads();
+            }
+            n_surv_total += n_surv;
+            // (2) the survivors in full
+            for (int base = 0; base < n_surv; base += blockDim.x) {
+                const int t = base + tid;
+                bool accept = false;
+                float crit2 = 0.f;
+                unsigned ia = 0, ib = 0;
+                if (t < n_surv) {
+                    const unsigned idx = (unsigned)s_surv[t];
+                    ia = idx / nb_u, ib = idx - ia * nb_u;
+                    accept = score_pair<false>(pc, s_pa[ia], s_pb[ib], crit2);
+                }
+                int pos;
+                const int total = place(accept, n_cand, pos);
+                if (accept) {
+                    if (pos < capC) {
+                        Cand cd;
+                        cd.i1 = ofs_a + (int)ia, cd.i2 = ofs_b + (int)ib, cd.s = crit2;
+                        cand0[pos] = cd;
+                    } else
+                        overflow = 1;
+                }
+                n_cand += total;
+                __syncthreads();
+            }
         }
+        if (tid == 0) atomicAdd(p.stats + frame * 4 + 3, n_surv_total);
         if (__syncthreads_or(overflow)) {
             if (tid == 0) atomicOr(p.flags + frame, OPP_FLAG_CAND_OVERFLOW);
             n_cand = min(n_cand, capC);
@@ -1813,18 +1982,31 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
         if (n_cand > 1) {
             int tie = 0;
             if (n_cand <= 4096) {
-                for (int t = tid; t < n_cand; t += blockDim.x) {
-                    const float s = cand0[t].s;
-                    int rank = 0;
-                    for (int u = 0; u < n_cand; ++u) {
-                        const float su = cand0[u].s;
-                        rank += (su > s);
-                        tie |= (su == s && u != t);
+                // rank by (score descending, position ascending): the order itself when no two scores are equal, and
+                // the stable order = what __final_insertion_sort leaves when run after the partition rounds below
+                auto rank_sort = [&]() {
+                    int any_tie = 0;
+                    for (int t = tid; t < n_cand; t += blockDim.x) {
+                        const float s = cand0[t].s;
+                        int rank = 0;
+                        for (int u = 0; u < n_cand; ++u) {
+                            const float su = cand0[u].s;
+                            rank += (su > s) | (su == s && u < t);
+                            any_tie |= (su == s && u != t);
+                        }
+                        cand1[rank] = cand0[t];
                     }
-                    cand1[rank] = cand0[t];
-                }
-                tie = __syncthreads_or(tie);
+                    return __syncthreads_or(any_tie);
+                };
+                tie = rank_sort();
                 sorted = cand1;
+                if (tie && p.cand_in_smem && n_cand <= 0xffff) {
+                    // tied scores: std::sort's element movement decides.  cand1 serves as scratch in between.
+                    unsigned short *pos_a = reinterpret_cast<unsigned short *>(cand1), *pos_b = pos_a + n_cand;
+                    std_sort_partition_rounds(cand0, n_cand, pos_a, pos_b, reinterpret_cast<int *>(smem_raw + p.off_surv));
+                    rank_sort();
+                    tie = 0;
+                }
             } else
                 tie = 1;
             if (tie) {
@@ -1835,9 +2017,81 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
         }
 
         stamp(p, frame, pair_id, 3);
-        // ---- greedy matching in sorted order (src/paf.cpp:154-173)
-        if (tid == 0) {
-            opp_conn_t *conns = p.conns + ((size_t)frame * OPP_N_PAIRS + pair_id) * capP;
+        // ---- greedy matching in sorted order (src/paf.cpp:154-173): a candidate is accepted unless an accepted one
+        // before it shares a peak.  Parallel form: among the candidates still undecided, one that is the FIRST (in
+        // sorted order) for both of its peaks has no undecided predecessor sharing a peak - and none of the accepted
+        // ones does, or it would have been rejected - so the sequential loop accepts it; accepting it rejects every
+        // other undecided candidate on its two peaks.  Rounds of (first-per-peak by atomicMin, accept, reject) decide
+        // all candidates in a handful of rounds on real frames; the position in sorted order is the only priority, so
+        // ties in the scores change nothing here.  Whatever is still undecided after GREEDY_ROUNDS is finished by the
+        // sequential loop; the accepted candidates are then written in sorted (= acceptance) order.
+        opp_conn_t *conns = p.conns + ((size_t)frame * OPP_N_PAIRS + pair_id) * capP;
+        constexpr int GREEDY_ROUNDS = 6;
+        unsigned char *s_state = reinterpret_cast<unsigned char *>(smem_raw + p.off_surv); // [n_cand] 0 undecided, 1 accepted, 2 rejected
+        if (n_cand > 32 && n_cand <= p.surv_cap * 4) {
+            int *s_first = s_ka; // [2 capP] first undecided candidate of every peak (the key lists are dead by now)
+            for (int t = tid; t < n_cand; t += blockDim.x) s_state[t] = 0;
+            int left = 1;
+            for (int round = 0; round < GREEDY_ROUNDS && left; ++round) {
+                for (int t = tid; t < 2 * capP; t += blockDim.x) s_first[t] = 0x7fffffff;
+                __syncthreads();
+                for (int t = tid; t < n_cand; t += blockDim.x)
+                    if (!s_state[t]) {
+                        atomicMin(&s_first[sorted[t].i1 - ofs_a], t);
+                        atomicMin(&s_first[capP + sorted[t].i2 - ofs_b], t);
+                    }
+                __syncthreads();
+                for (int t = tid; t < n_cand; t += blockDim.x)
+                    if (!s_state[t]) {
+                        const int la = sorted[t].i1 - ofs_a, lb = sorted[t].i2 - ofs_b;
+                        if (s_first[la] == t && s_first[capP + lb] == t) s_state[t] = 1, s_used[la] = 1, s_used[capP + lb] = 1;
+                    }
+                __syncthreads();
+                left = 0;
+                for (int t = tid; t < n_cand; t += blockDim.x)
+                    if (!s_state[t]) {
+                        if (s_used[sorted[t].i1 - ofs_a] | s_used[capP + sorted[t].i2 - ofs_b]) s_state[t] = 2;
+                        else left = 1;
+                    }
+                left = __syncthreads_or(left);
+            }
+            if (left) { // long chains of candidates, each blocked only by its predecessor: the rest in sequence
+                if (tid == 0)
+                    for (int t = 0; t < n_cand; ++t)
+                        if (!s_state[t]) {
+                            const int la = sorted[t].i1 - ofs_a, lb = sorted[t].i2 - ofs_b;
+                            if (s_used[la] | s_used[capP + lb]) continue;
+                            s_used[la] = 1, s_used[capP + lb] = 1, s_state[t] = 1;
+                        }
+                __syncthreads();
+            }
+            int nc = 0;
+            for (int base = 0; base < n_cand; base += blockDim.x) {
+                const int t = base + tid;
+                const bool acc = t < n_cand && s_state[t] == 1;
+                const unsigned m = __ballot_sync(0xffffffffu, acc);
+                if (lane == 0) s_misc[warp] = __popc(m);
+                __syncthreads();
+                int before = nc, total = 0;
+                for (int q = 0; q < nwarps; ++q) {
+                    const int cq = s_misc[q];
+                    if (q < warp) before += cq;
+                    total += cq;
+                }
+                if (acc) {
+                    const Cand cd = sorted[t];
+                    opp_conn_t cn;
+                    cn.cid1 = cd.i1, cn.cid2 = cd.i2, cn.score = cd.s;
+                    conns[before + __popc(m & ((1u << lane) - 1))] = cn; // at most min(na, nb) <= capP are accepted
+                }
+                nc += total;
+                __syncthreads();
+            }
+            if (tid == 0) {
+                p.n_conns[frame * OPP_N_PAIRS + pair_id] = nc;
+                atomicAdd(p.stats + frame * 4 + 2, n_cand);
+            }
+        } else if (tid == 0) {
             int nc = 0;
             for (int t = 0; t < n_cand; ++t) {
                 const Cand cd = sorted[t];

@@ -73,10 +73,13 @@ struct K3Params {
     int *flags;            // [n] device flag words, OR-ed by every stage
     int *flags_out;        // [n] optional: final flag word of the frame, written once by the assembly (may be mapped host memory)
     int *href_parts;       // [n][capH][18]
-    int *stats;            // [n][4] partial humans, merges, total candidates, total pairs
+    int *stats;            // [n][4] partial humans, merges, total candidates, pairs that passed the quick PAF test
     int paf_in_smem, cand_in_smem, score_in_smem, conns_in_smem, owner_in_smem;
     // shared-memory carve-up (byte offsets)
     int off_paf, off_pk, off_cand, off_used, off_misc, off_keys, off_href, off_score, off_conn, off_keep, off_owner;
+    int off_cand1;          // second candidate buffer (shares its bytes with the PAF tile, which is dead by then)
+    int conn_cap, pk_cap;   // entries of the assembly's staging areas for connections / peaks (frames beyond them: slower forms)
+    int off_surv, surv_cap; // [surv_cap] ints: pairs that passed the quick PAF test (then, as bytes, the matching's per-candidate state)
     float thr_vec, thr_human;
     // completion word for the latency path: every frame's assembly bumps batch_done; the one that completes the batch
     // writes done_tag to host_done (mapped pinned memory) after a system-scope fence, so the host can spin on it
