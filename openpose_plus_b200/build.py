@@ -33,7 +33,33 @@ def build(force=False, verbose=False):
         return OUT
     cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
     subprocess.run(cmd, check=True)
+    check_sass()
     return OUT
+
+
+CUOBJDUMP = os.path.join(os.path.dirname(NVCC), "cuobjdump")
+
+
+def fused_multiply_adds(lib=None):
+    """{kernel: count} of fused multiply-adds (FFMA, FFMA2, HFMA2 excluded) in the SASS of the resize / peak kernels.
+    Bit-exactness with the reference's scalar filter rests on every product being rounded before it is added: the
+    library is built with -fmad=false and the packed adds (add.rn.f32x2) are fed by scalar multiplications only, but
+    ptxas is known to contract a packed multiply feeding a packed add into FFMA2 regardless, so the SASS is checked.
+    (The limb kernel's IEEE divisions and square roots expand to FFMA sequences: those are the correctly rounded forms.)"""
+    out = subprocess.run([CUOBJDUMP, "-sass", lib or OUT], check=True, capture_output=True, text=True).stdout
+    counts, fn = {}, None
+    for line in out.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+        elif fn and ("FFMA" in line or "DFMA" in line) and any(k in fn for k in ("k0_", "k1_", "k2_")):
+            counts[fn] = counts.get(fn, 0) + 1
+    return counts
+
+
+def check_sass():
+    bad = fused_multiply_adds()
+    if bad:
+        raise RuntimeError("fused multiply-adds in kernels that must round every product: %r" % bad)
 
 
 REF_INCLUDE = "/root/reference/include"

@@ -431,10 +431,17 @@ struct Win9 {
 
 // Operands for cell i of n along one axis: (m2, m1, z, p1, p2) = cells i-2 .. i+2 (anything where the cell does
 // not exist: such a value is never selected).  NB = neighbour depth (1: R <= S, 2: S < R <= 2S; needs n >= NB + 1).
-template <int NB, bool BZ>
+// INTERIOR: the caller knows NB <= i < n - NB, so every operand is the plain neighbour (no selects, and the *s operands
+// are the same values as their neighbours: their tap products merge).
+template <int NB, bool BZ, bool INTERIOR = false>
 __device__ __forceinline__ Win9 make_win(float m2, float m1, float z, float p1, float p2, int i, int n)
 {
     Win9 v;
+    if (INTERIOR) {
+        v.b = z, v.a = v.as = m1, v.c = v.cs = p1;
+        v.a2 = v.a2s = NB > 1 ? m2 : 0.f, v.c2 = v.c2s = NB > 1 ? p2 : 0.f;
+        return v;
+    }
     const bool lo1 = i > 0, hi1 = i < n - 1;
     v.b = z;
     if (BZ) {
@@ -510,6 +517,59 @@ __device__ __forceinline__ void col_all(const float *__restrict__ k, const Win9 
 {
 #pragma unroll
     for (int ph = 0; ph < S; ++ph) s[ph] = col_phase<S, R>(k, ph, v);
+}
+
+// The column pass of a thread's TWO image columns at once with sm_100's packed FP32 adds (add.rn.f32x2, SASS FADD2:
+// two independent IEEE additions per instruction).  The additions are two thirds of the filter's arithmetic and the
+// peak kernel is FP32-issue bound whenever most blocks are active.  Every lane of a packed add is the same
+// round-to-nearest addition on the same operands as the scalar form; the products stay scalar multiplications, so
+// there is no multiply feeding a packed add inside one instruction stream that ptxas could contract into FFMA2
+// (build.py greps the SASS for FFMA2 / FFMA to make sure).
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi)
+{
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b)
+{
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// RowFilter (taps left to right) for two neighbouring outputs per packed add: the same scalar products, the same
+// additions in the same order, two chains per instruction.
+template <int S, int R>
+__device__ __forceinline__ void row_taps2(const float *__restrict__ k, const Win9 &v, float (&out)[S])
+{
+    static_assert(S % 2 == 0, "output pairs");
+#pragma unroll
+    for (int q = 0; q < S; q += 2) {
+        f32x2_t s = pack2(__fmul_rn(k[0], win_src<S>(v, q - R)), __fmul_rn(k[0], win_src<S>(v, q + 1 - R)));
+#pragma unroll
+        for (int j = 1; j <= 2 * R; ++j) s = add2(s, pack2(__fmul_rn(k[j], win_src<S>(v, q + j - R)), __fmul_rn(k[j], win_src<S>(v, q + 1 + j - R))));
+        unpack2(s, out[q], out[q + 1]);
+    }
+}
+
+template <int S, int R>
+__device__ __forceinline__ void col_all2(const float *__restrict__ k, const Win9 &v0, const Win9 &v1, float (&s0)[S], float (&s1)[S])
+{
+#pragma unroll
+    for (int ph = 0; ph < S; ++ph) {
+        f32x2_t s = pack2(__fmul_rn(k[R], v0.b), __fmul_rn(k[R], v1.b));
+#pragma unroll
+        for (int j = 1; j <= R; ++j) {
+            const f32x2_t ps = add2(pack2(win_src<S>(v0, ph + j), win_src<S>(v1, ph + j)), pack2(win_src<S>(v0, ph - j), win_src<S>(v1, ph - j)));
+            float p0, p1;
+            unpack2(ps, p0, p1);
+            s = add2(s, pack2(__fmul_rn(k[R + j], p0), __fmul_rn(k[R + j], p1)));
+        }
+        unpack2(s, s0[ph], s1[ph]);
+    }
 }
 
 #ifndef K2_FAST_MAX_THREADS
@@ -689,10 +749,18 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
             const int r = it / ncol, c = jlo + (it - r * ncol);
             if (!((s_need[r] >> (c - jlo)) & 1ull)) continue; // no active block reads this cell
             const float *Lr = L + r * w;
-            const Win9 win = make_win<NB, BZ>(NB > 1 ? Lr[max(c - 2, 0)] : 0.f, Lr[max(c - 1, 0)], Lr[c], Lr[min(c + 1, w - 1)],
-                                              NB > 1 ? Lr[min(c + 2, w - 1)] : 0.f, c, w);
             float out[S];
-            row_taps<S, R, BZ>(p.taps, win, out);
+            const float m2 = NB > 1 ? Lr[max(c - 2, 0)] : 0.f, m1 = Lr[max(c - 1, 0)], p1 = Lr[min(c + 1, w - 1)], p2 = NB > 1 ? Lr[min(c + 2, w - 1)] : 0.f;
+            constexpr bool kRowPacked = R > 2 || BZ; // the symmetric-small forms (k = 3, 5) stay as OpenCV writes them
+            if (c >= NB && c + NB < w) { // interior cell: plain neighbours
+                const Win9 win = make_win<NB, BZ, true>(m2, m1, Lr[c], p1, p2, c, w);
+                if (kRowPacked) row_taps2<S, R>(p.taps, win, out);
+                else row_taps<S, R, BZ>(p.taps, win, out);
+            } else {
+                const Win9 win = make_win<NB, BZ>(m2, m1, Lr[c], p1, p2, c, w);
+                if (kRowPacked) row_taps2<S, R>(p.taps, win, out);
+                else row_taps<S, R, BZ>(p.taps, win, out);
+            }
             float *d = Rrow + r * RW + S * (c - jlo);
             if (S % 4 == 0) {
 #pragma unroll
@@ -769,10 +837,15 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
         };
         auto smooth_rows = [&](int i, float (&s0)[S], float (&s1)[S]) { // the S image rows of feature row i, both columns
             w0[NW - 1] = ldr0(i + NB), w1[NW - 1] = ldr1(i + NB);
-            const Win9 v0 = make_win<NB, BZ>(w0[0], w0[NB - 1], w0[NB], w0[NB + 1], w0[NW - 1], i, h);
-            const Win9 v1 = make_win<NB, BZ>(w1[0], w1[NB - 1], w1[NB], w1[NB + 1], w1[NW - 1], i, h);
-            col_all<S, R>(p.taps, v0, s0);
-            col_all<S, R>(p.taps, v1, s1);
+            if (i >= NB && i + NB < h) { // interior feature row (all but NB at either end): plain neighbours, no selects
+                const Win9 v0 = make_win<NB, BZ, true>(w0[0], w0[NB - 1], w0[NB], w0[NB + 1], w0[NW - 1], i, h);
+                const Win9 v1 = make_win<NB, BZ, true>(w1[0], w1[NB - 1], w1[NB], w1[NB + 1], w1[NW - 1], i, h);
+                col_all2<S, R>(p.taps, v0, v1, s0, s1);
+            } else {
+                const Win9 v0 = make_win<NB, BZ>(w0[0], w0[NB - 1], w0[NB], w0[NB + 1], w0[NW - 1], i, h);
+                const Win9 v1 = make_win<NB, BZ>(w1[0], w1[NB - 1], w1[NB], w1[NB + 1], w1[NW - 1], i, h);
+                col_all2<S, R>(p.taps, v0, v1, s0, s1);
+            }
         };
         const int i_first = ia > 0 ? ia - 1 : ia;
         load_window(i_first);
@@ -821,10 +894,21 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
                 stale = false;
             }
             smooth_rows(i, s0, s1);
+            // A feature row whose 64 x S smoothed pixels all stay <= thresh holds no peak and cannot outrank one: it
+            // counts as -inf for the rows around it, exactly like a block the activity analysis ruled out - but decided
+            // on the smoothed values themselves.  The 3x3 max (shuffles, compares, masks: half of this loop's
+            // instructions, all on the ALU pipe) is then skipped; on maps with a noise floor that is most rows.
+            float mx = fmaxf(s0[0], s1[0]);
 #pragma unroll
-            for (int ph = 0; ph < S; ++ph) step(s0[ph], s1[ph], ph, true);
-            flush(S * i);
-            open = true;
+            for (int ph = 1; ph < S; ++ph) mx = fmaxf(mx, fmaxf(s0[ph], s1[ph]));
+            if (__any_sync(0xffffffffu, mx > p.thresh)) {
+#pragma unroll
+                for (int ph = 0; ph < S; ++ph) step(s0[ph], s1[ph], ph, true);
+                flush(S * i);
+                open = true;
+            } else if (open) {
+                close_block(S * i);
+            }
             shift_window();
         }
         if (ib < h && active(ib)) { // halo row below the tile: its first image row closes the last row of the tile

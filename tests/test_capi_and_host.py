@@ -511,3 +511,14 @@ def test_gather_results_ships_only_the_humans_found():
     assert np.array_equal(back[0]["score"], want["score"]) and np.array_equal(back[1], cc)
     empty = _expand(_compact((np.zeros((0, 4), capi.HUMAN_DT), np.zeros(0, np.int32), np.zeros(0, np.int32))))
     assert empty[0].shape == (0, 4)
+
+
+def test_no_fused_multiply_add_in_the_filter_kernels():
+    """The resize / peak kernels must round every product before adding it (bit-exactness with cv::GaussianBlur's scalar
+    path): no FFMA / FFMA2 in their SASS - in particular none contracted from the packed adds' operands."""
+    from openpose_plus_b200 import build
+    if not os.path.exists(build.CUOBJDUMP):
+        pytest.skip("cuobjdump not available")
+    assert build.fused_multiply_adds() == {}
+    sass = subprocess.run([build.CUOBJDUMP, "-sass", build.OUT], check=True, capture_output=True, text=True).stdout
+    assert "FADD2" in sass  # the packed adds are really there
