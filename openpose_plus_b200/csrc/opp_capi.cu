@@ -231,6 +231,14 @@ void plan_k3_smem(opp_handle_s *h)
     size_t surv_ints = 1024;
     if (p.cand_in_smem && (size_t)capC > surv_ints * 4) surv_ints = ((size_t)capC + 3) / 4;
     p.off_surv = (int)off, p.surv_cap = (int)surv_ints, off += align_up(surv_ints * sizeof(int), 16);
+    p.cand_unordered = p.cand_in_smem && capC <= 4096;
+    const size_t n_steps = (size_t)std::max(g.H, g.W);
+    p.steps_in_smem = n_steps <= 1024;
+    p.off_steps = (int)off;
+    if (p.steps_in_smem) off += align_up(n_steps * sizeof(float), 16);
+    p.weak_in_smem = p.paf_in_smem && p.cand_unordered;
+    p.off_weak = (int)off;
+    if (p.weak_in_smem) off += align_up((((size_t)g.h * g.w + 31) / 32) * sizeof(unsigned), 16);
     const size_t phase1 = off;
     // assembly phase (re-uses the same bytes): partial humans, survivors, connections, peak x/y/score
     off = 0;

@@ -1140,9 +1140,43 @@ struct Cand {
 struct PairCtx {
     const float *px, *py; // the limb's x / y PAF planes (feature resolution)
     const OppGeom *g;
+    const float *steps;   // [max(H, W)] d -> (float)d / 10.f (IEEE), or null: the STEP_X / STEP_Y divisions as a table
+    const unsigned *weak; // bit per feature cell: |px| + |py| so small that no sample there can exceed THRESH_VECTOR_SCORE (or null)
     int w, H, sshift;
     float thr;
 };
+
+// roundpaf for 0 <= v < 2^22 without conversion instructions (F2I / I2F run on the quarter-rate XU pipe, and the pair
+// filter rounds eight coordinates per pair): v + 2^23 rounds v to the nearest integer, ties to even; floor(v + 0.5) -
+// what (int)((double)v + 0.5) is for v >= 0 - differs from that only at a tie that went down, where v - r = +0.5.
+__device__ __forceinline__ int round_paf_small(float v)
+{
+    const float r = __fadd_rn(v, 8388608.f);
+    const float d = __fsub_rn(v, __fsub_rn(r, 8388608.f)); // exact
+    return (__float_as_int(r) - 0x4B000000) + (d >= 0.5f ? 1 : 0);
+}
+
+// First stage of the pair filter at power-of-two scales: the four middle samples' CELLS only.  A sample's score is
+// v . paf(cell) with |v.x|, |v.y| <= 1 + 2^-23, so in a cell with |px| + |py| <= thresh (1 - 2^-13) it cannot exceed the
+// threshold whatever the direction: two such samples rule the pair out (cnt <= 8).  No square root, no division, no
+// PAF load - and most pairs of a crowded frame join peaks of different people across empty PAF.
+__device__ __forceinline__ bool pair_may_pass(const PairCtx &c, const int2 A, const int2 B)
+{
+    const int dx = B.x - A.x, dy = B.y - A.y;
+    if ((dx | dy) == 0) return false;
+    const float step_x = c.steps ? copysignf(c.steps[abs(dx)], (float)dx) : __fdiv_rn((float)dx, 10.f);
+    const float step_y = c.steps ? copysignf(c.steps[abs(dy)], (float)dy) : __fdiv_rn((float)dy, 10.f);
+    const float ax = (float)A.x, ay = (float)A.y;
+    int weak = 0;
+#pragma unroll
+    for (int i = 3; i < 7; ++i) {
+        const int lx = round_paf_small(__fadd_rn(ax, __fmul_rn((float)i, step_x)));
+        const int ly = round_paf_small(__fadd_rn(ay, __fmul_rn((float)i, step_y)));
+        const int cell = (ly >> c.sshift) * c.w + (lx >> c.sshift);
+        weak += (c.weak[cell >> 5] >> (cell & 31)) & 1u;
+    }
+    return weak < 2;
+}
 
 template <bool QUICK>
 __device__ __forceinline__ bool score_pair(const PairCtx &c, const int2 A, const int2 B, float &crit2)
@@ -1155,7 +1189,9 @@ __device__ __forceinline__ bool score_pair(const PairCtx &c, const int2 A, const
     if (l2 == 0) return false; // `norm < 1e-12` is true only for coincident peaks
     const float norm = l2 < (1 << 24) ? __fsqrt_rn((float)l2) : (float)sqrt((double)l2);
     const float vx = __fdiv_rn((float)dx, norm), vy = __fdiv_rn((float)dy, norm);
-    const float step_x = __fdiv_rn((float)dx, 10.f), step_y = __fdiv_rn((float)dy, 10.f); // :321-322
+    // STEP_X, STEP_Y = d / 10.f  (:321-322); division rounds symmetrically, so the table of |d| serves both signs
+    const float step_x = c.steps ? copysignf(c.steps[abs(dx)], (float)dx) : __fdiv_rn((float)dx, 10.f);
+    const float step_y = c.steps ? copysignf(c.steps[abs(dy)], (float)dy) : __fdiv_rn((float)dy, 10.f);
     float scores = 0.f;
     int cnt = 0;
 #pragma unroll
@@ -1980,6 +2016,10 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
             px_plane = s_paf, py_plane = s_paf + h * w;
         }
         for (int t = tid; t < 2 * capP; t += blockDim.x) s_used[t] = 0;
+        if (p.steps_in_smem) { // d / 10.f for every coordinate difference the image allows
+            float *st = reinterpret_cast<float *>(smem_raw + p.off_steps);
+            for (int t = tid; t < max(p.g.H, p.g.W); t += blockDim.x) st[t] = __fdiv_rn((float)t, 10.f);
+        }
         if (tid < 16) s_misc[tid] = 0;
         stage_wait();
         __syncthreads(); // also publishes the mbarrier initialisation to the waiting threads
@@ -1989,7 +2029,106 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
         PairCtx pc;
         pc.px = px_plane, pc.py = py_plane, pc.g = &p.g, pc.w = w, pc.H = p.g.H, pc.thr = p.thr_vec;
         pc.sshift = (p.g.S > 0 && (p.g.S & (p.g.S - 1)) == 0) ? 31 - __clz(p.g.S) : -1;
-        int overflow = 0;
+        pc.steps = p.steps_in_smem ? reinterpret_cast<const float *>(smem_raw + p.off_steps) : nullptr;
+        pc.weak = nullptr;
+        if (p.weak_in_smem && pc.sshift >= 0 && p.g.W < (1 << 22) && p.g.H < (1 << 22)) {
+            // cells whose PAF is too small for any sample to pass (see pair_may_pass)
+            unsigned *wk = reinterpret_cast<unsigned *>(smem_raw + p.off_weak);
+            const float tw = __fmul_rn(p.thr_vec, 1.f - 1.f / 8192.f);
+            for (int base = warp * 32; base < h * w; base += blockDim.x) {
+                const int cidx = base + lane;
+                const bool wkb = cidx >= h * w || __fadd_rn(fabsf(px_plane[cidx]), fabsf(py_plane[cidx])) <= tw;
+                const unsigned m = __ballot_sync(0xffffffffu, wkb);
+                if (lane == 0) wk[base >> 5] = m;
+            }
+            pc.weak = wk;
+            __syncthreads();
+        }
+        int *s_surv = reinterpret_cast<int *>(smem_raw + p.off_surv); // [surv_cap] pairs that passed the quick test
+        const unsigned n_pairs_u = (unsigned)n_pairs, nb_u = (unsigned)nb;
+        const unsigned lt = (1u << lane) - 1;
+        // idx -> (ia, ib) without an integer division: q = floor(idx * floor(2^32 / nb) / 2^32) is ia or ia - 1
+        const unsigned nb_inv = nb_u > 1 ? (unsigned)(0x100000000ull / nb_u) : 0u;
+        auto split = [&](unsigned idx, unsigned &ia, unsigned &ib) {
+            if (nb_u == 1) {
+                ia = idx, ib = 0;
+                return;
+            }
+            ia = __umulhi(idx, nb_inv);
+            ib = idx - ia * nb_u;
+            if (ib >= nb_u) ib -= nb_u, ++ia;
+        };
+        int overflow = 0, n_surv_total = 0;
+        if (p.cand_unordered) {
+            // Candidates are appended in whatever order the warps finish (one shared-memory atomic per warp and round,
+            // no block-wide compaction); the sort below ranks them by (score, pair index), which is std::sort's
+            // result whenever no two scores are equal, and restores the a-major / b-minor input order first when some are.
+            int *s_cnt = s_misc + 12; // [0] survivors in the list, [1] candidates appended
+            if (tid == 0) s_cnt[0] = 0, s_cnt[1] = 0;
+            __syncthreads();
+            auto drain = [&]() { // the listed survivors in full; whole CTA
+                __syncthreads();
+                const int n_surv = min(s_cnt[0], p.surv_cap);
+                n_surv_total += n_surv;
+                for (int base = warp * 32; base < n_surv; base += blockDim.x) {
+                    const int t = base + lane;
+                    bool accept = false;
+                    float crit2 = 0.f;
+                    unsigned ia = 0, ib = 0;
+                    if (t < n_surv) {
+                        split((unsigned)s_surv[t], ia, ib);
+                        accept = score_pair<false>(pc, s_pa[ia], s_pb[ib], crit2);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, accept);
+                    if (m) {
+                        int base_pos = 0;
+                        if (lane == 0) base_pos = atomicAdd(&s_cnt[1], __popc(m));
+                        base_pos = __shfl_sync(0xffffffffu, base_pos, 0);
+                        if (accept) {
+                            const int pos = base_pos + __popc(m & lt);
+                            if (pos < capC) {
+                                Cand cd;
+                                cd.i1 = ofs_a + (int)ia, cd.i2 = ofs_b + (int)ib, cd.s = crit2;
+                                cand0[pos] = cd;
+                            } else
+                                overflow = 1;
+                        }
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) s_cnt[0] = 0;
+                __syncthreads();
+            };
+            const unsigned chunk = (unsigned)(p.surv_cap / 2) & ~255u; // pairs per round of quick tests: the list never overflows
+            unsigned listed_max = 0;                                    // upper bound of the survivors listed so far
+            for (unsigned c0 = 0; c0 < n_pairs_u; c0 += chunk) {
+                const unsigned c1 = min(c0 + chunk, n_pairs_u);
+                if (listed_max + (c1 - c0) > (unsigned)p.surv_cap) {
+                    drain();
+                    listed_max = 0;
+                }
+                for (unsigned base = c0 + warp * 32; base < c1; base += blockDim.x) {
+                    const unsigned idx = base + lane;
+                    bool alive = false;
+                    if (idx < c1) {
+                        unsigned ia, ib;
+                        split(idx, ia, ib);
+                        float unused;
+                        alive = pc.weak ? pair_may_pass(pc, s_pa[ia], s_pb[ib]) : score_pair<true>(pc, s_pa[ia], s_pb[ib], unused);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, alive);
+                    if (m) {
+                        int base_pos = 0;
+                        if (lane == 0) base_pos = atomicAdd(&s_cnt[0], __popc(m));
+                        base_pos = __shfl_sync(0xffffffffu, base_pos, 0);
+                        if (alive) s_surv[base_pos + __popc(m & lt)] = (int)idx;
+                    }
+                }
+                listed_max += c1 - c0;
+            }
+            drain();
+            n_cand = s_cnt[1];
+        } else {
         // ordered block compaction: the threads with `flag` learn their position after the `count` entries already
         // there, in thread order (candidates must stay a-major / b-minor: it is std::sort's input order)
         auto place = [&](bool flag, int count, int &pos) -> int {
@@ -2002,13 +2141,10 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
                 if (q < warp) before += cq;
                 total += cq;
             }
-            pos = before + __popc(m & ((1u << lane) - 1));
+            pos = before + __popc(m & lt);
             return total;
         };
-        int *s_surv = reinterpret_cast<int *>(smem_raw + p.off_surv); // [surv_cap] pairs that passed the quick test, in order
-        const unsigned n_pairs_u = (unsigned)n_pairs, nb_u = (unsigned)nb;
         unsigned next = 0;
-        int n_surv_total = 0;
         while (next < n_pairs_u) {
             // (1) quick test of the next pairs until the survivor list is (nearly) full
             int n_surv = 0;
@@ -2016,7 +2152,8 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
                 const unsigned idx = next + tid;
                 bool alive = false;
                 if (idx < n_pairs_u) {
-                    const unsigned ia = idx / nb_u, ib = idx - ia * nb_u;
+                    unsigned ia, ib;
+                    split(idx, ia, ib);
                     float unused;
                     alive = score_pair<true>(pc, s_pa[ia], s_pb[ib], unused);
                 }
@@ -2035,8 +2172,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
                 float crit2 = 0.f;
                 unsigned ia = 0, ib = 0;
                 if (t < n_surv) {
-                    const unsigned idx = (unsigned)s_surv[t];
-                    ia = idx / nb_u, ib = idx - ia * nb_u;
+                    split((unsigned)s_surv[t], ia, ib);
                     accept = score_pair<false>(pc, s_pa[ia], s_pb[ib], crit2);
                 }
                 int pos;
@@ -2053,11 +2189,12 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
                 __syncthreads();
             }
         }
+        }
         if (tid == 0) atomicAdd(p.stats + frame * 4 + 3, n_surv_total);
         if (__syncthreads_or(overflow)) {
             if (tid == 0) atomicOr(p.flags + frame, OPP_FLAG_CAND_OVERFLOW);
-            n_cand = min(n_cand, capC);
         }
+        n_cand = min(n_cand, capC);
         stamp(p, frame, pair_id, 2);
 
         // ---- sort by score, descending, in std::sort's order.  With no equal scores the sorted order is
@@ -2084,6 +2221,20 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
                 };
                 tie = rank_sort();
                 sorted = cand1;
+                if (tie && p.cand_unordered) {
+                    // std::sort's input is the candidate list in a-major / b-minor order (src/paf.cpp:93-131): put the
+                    // unordered list into that order first (rank by pair index, which is unique), back into cand0
+                    for (int t = tid; t < n_cand; t += blockDim.x) {
+                        const Cand ct = cand0[t];
+                        const unsigned key = (unsigned)(ct.i1 - ofs_a) * nb_u + (unsigned)(ct.i2 - ofs_b);
+                        int rank = 0;
+                        for (int u = 0; u < n_cand; ++u) rank += ((unsigned)(cand0[u].i1 - ofs_a) * nb_u + (unsigned)(cand0[u].i2 - ofs_b)) < key;
+                        cand1[rank] = ct;
+                    }
+                    __syncthreads();
+                    for (int t = tid; t < n_cand; t += blockDim.x) cand0[t] = cand1[t];
+                    __syncthreads();
+                }
                 if (tie && p.cand_in_smem && n_cand <= 0xffff) {
                     // tied scores: std::sort's element movement decides.  cand1 serves as scratch in between.
                     unsigned short *pos_a = reinterpret_cast<unsigned short *>(cand1), *pos_b = pos_a + n_cand;

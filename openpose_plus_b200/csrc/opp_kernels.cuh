@@ -79,6 +79,9 @@ struct K3Params {
     int off_paf, off_pk, off_cand, off_used, off_misc, off_keys, off_href, off_score, off_conn, off_keep, off_owner;
     int off_cand1;          // second candidate buffer (shares its bytes with the PAF tile, which is dead by then)
     int conn_cap, pk_cap;   // entries of the assembly's staging areas for connections / peaks (frames beyond them: slower forms)
+    int off_steps, steps_in_smem; // [max(H, W)] floats: d / 10.f, the PAF sampling steps as a table (built by every limb CTA)
+    int off_weak, weak_in_smem;   // [ceil(h w / 32)] words: feature cells whose PAF cannot lift a sample over THRESH_VECTOR_SCORE
+    int cand_unordered;           // candidates are appended without block-wide ordering (capC <= 4096, shared memory)
     int off_surv, surv_cap; // [surv_cap] ints: pairs that passed the quick PAF test (then, as bytes, the matching's per-candidate state)
     float thr_vec, thr_human;
     // completion word for the latency path: every frame's assembly bumps batch_done; the one that completes the batch

@@ -194,3 +194,39 @@ def test_fp32_forms_used_by_the_limb_kernel_equal_the_references_double_forms():
         inside = norm <= np.float32(0.5) * np.float32(H)
         pen = np.minimum(0.0, 0.5 * H / norm[inside].astype(np.float64) - 1.0)
         assert (pen == 0.0).all()
+
+
+def test_pair_prefilter_forms_of_the_limb_kernel():
+    """The limb kernel's first filter over (a, b) peak pairs (csrc/opp_kernels.cu pair_may_pass) rests on two facts,
+    checked here in IEEE float32:
+      (a) round_paf_small: for 0 <= v < 2^22, with r = v + 2^23 (ties to even) and d = v - (r - 2^23),
+          (int)((double)v + 0.5) == (bits(r) - 0x4B000000) + (d >= 0.5f)                       (roundpaf, src/paf.cpp:337)
+      (b) |v.x|, |v.y| <= 1 + 2^-23 for v = (dx / norm, dy / norm), norm = (float)sqrt((double)(dx^2 + dy^2)), so a sample
+          in a cell with |px| + |py| <= thr (1 - 2^-13) scores fl(fl(vx px) + fl(vy py)) <= thr: it can never count
+          towards `cnt` (src/paf.cpp:108-113), whatever the direction."""
+    f32 = np.float32
+    rng = np.random.default_rng(1)
+    v = np.concatenate([rng.uniform(0, 40000, 2_000_000), np.arange(0, 40000, 0.5), np.nextafter(np.arange(0.5, 40000, 1.0), 0),
+                        np.nextafter(np.arange(0.5, 40000, 1.0), 1e9), [0.0, 0.49999997, 0.5, 4194303.5, 4194303.0]]).astype(f32)
+    want = (v.astype(np.float64) + 0.5).astype(np.int64)
+    r = (v + f32(8388608.0)).astype(f32)
+    d = (v - (r - f32(8388608.0)).astype(f32)).astype(f32)
+    got = (r.view(np.int32).astype(np.int64) - 0x4B000000) + (d >= f32(0.5))
+    assert np.array_equal(got, want)
+    dd = np.arange(-1200, 1201, dtype=np.int64)
+    dx, dy = np.meshgrid(dd, dd)
+    dx, dy = dx.ravel(), dy.ravel()
+    keep = (dx != 0) | (dy != 0)
+    dx, dy = dx[keep], dy[keep]
+    norm = np.sqrt((dx * dx + dy * dy).astype(np.float64)).astype(f32)
+    vx, vy = (dx.astype(f32) / norm).astype(f32), (dy.astype(f32) / norm).astype(f32)
+    assert max(np.abs(vx).max(), np.abs(vy).max()) <= 1.0 + 2.0 ** -23
+    thr = f32(0.05)
+    tw = f32(thr * f32(1.0 - 1.0 / 8192.0))
+    # adversarial cell values on the bound: all of the magnitude in the axis the direction favours, and split evenly
+    idx = rng.integers(0, len(vx), 400_000)
+    for (px, py) in ((tw * np.sign(vx[idx]), 0 * vy[idx]), (0 * vx[idx], tw * np.sign(vy[idx])), (tw / 2 * np.sign(vx[idx]), tw / 2 * np.sign(vy[idx]))):
+        px, py = px.astype(f32), py.astype(f32)
+        assert ((np.abs(px) + np.abs(py)).astype(f32) <= tw).all()
+        score = ((vx[idx] * px).astype(f32) + (vy[idx] * py).astype(f32)).astype(f32)
+        assert not (score > thr).any()
