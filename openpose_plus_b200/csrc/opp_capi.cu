@@ -100,6 +100,7 @@ struct opp_handle_s {
     bool paf_early = true; // latency path: the limb kernel fetches its PAF tiles from pinned memory itself (OPP_NO_PAF_EARLY=1 disables)
     bool done_flag = true; // completion word in pinned memory on the latency path (OPP_NO_DONE_FLAG=1 disables)
     int tag_seq = 0;
+    bool generic_via_map = false; // non-integer scales: materialise the heat map first and let the generic kernel read it
     bool generic_rep = true; // integer scales outside the fast kernel's range: replication-aware generic kernel (OPP_NO_GENERIC_REP=1: via the materialised map)
     bool stage_pageable = true; // latency path for pageable inputs through pinned staging (OPP_NO_STAGE_PAGEABLE=1: cudaMemcpyAsync from pageable memory)
     bool pdl = true; // programmatic dependent launch on the latency path (OPP_NO_PDL=1 disables)
@@ -616,6 +617,7 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
         h->pdl = getenv("OPP_NO_PDL") == nullptr;
         h->stage_pageable = getenv("OPP_NO_STAGE_PAGEABLE") == nullptr;
         h->generic_rep = getenv("OPP_NO_GENERIC_REP") == nullptr;
+        h->generic_via_map = getenv("OPP_GENERIC_VIA_MAP") != nullptr && atoi(getenv("OPP_GENERIC_VIA_MAP")) != 0;
         h->done_flag = getenv("OPP_NO_DONE_FLAG") == nullptr;
         h->paf_early = getenv("OPP_NO_PAF_EARLY") == nullptr;
         if (const char *e = getenv("OPP_ZC_IN_MAX")) h->zero_copy_in_max = atoi(e);
@@ -750,7 +752,9 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     // the generic peak kernel reads a materialised heat map only at non-integer scales; at an integer scale its
     // replication-aware form works from the feature maps like the fast kernel
     const bool generic_rep = !h->fast_k2 && g.S > 0 && h->generic_rep;
-    const bool generic_needs_conf_up = !h->fast_k2 && !generic_rep;
+    // non-integer scales: the generic peak kernel builds its tiles from the feature maps (OPP_GENERIC_VIA_MAP=1: from a
+    // materialised heat map, the first form of this path)
+    const bool generic_needs_conf_up = !h->fast_k2 && !generic_rep && h->generic_via_map;
     bool forked = false;
     auto resize_on = [&](cudaStream_t rs, const float *src, float *dst, int C, int layout) -> int {
         K1Params k1{};

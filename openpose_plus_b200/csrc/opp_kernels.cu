@@ -308,6 +308,58 @@ __global__ void __launch_bounds__(OPP_THREADS) k1_general(const K1Params p)
     }
 }
 
+// Any scale, channels-first: cv::resize's own structure.  One CTA per (block of output rows, plane, frame): the feature
+// rows under the block are resized horizontally ONCE into shared memory (cv's row buffers: S[sx] a0 + S[sx+1] a1), every
+// output row is then the vertical blend of two of them (r0 b0 + r1 b1), written with coalesced streaming stores.
+// Same operations on the same operands as upsample_at; store-bound like the replication kernels.
+#define K1G_ROWS 32
+__global__ void __launch_bounds__(OPP_THREADS) k1_general_chw(const K1Params p)
+{
+    extern __shared__ __align__(16) float smem[];
+    const OppGeom &g = p.g;
+    const int W = g.W, H = g.H, h = g.h, w = g.w;
+    int c = blockIdx.y;
+    const float *src = p.src;
+    float *dst = p.dst;
+    int C = p.C;
+    if (c >= p.C) c -= p.C, src = p.src2, dst = p.dst2, C = p.C2;
+    const int f = blockIdx.z, y_a = blockIdx.x * K1G_ROWS, y_b = min(y_a + K1G_ROWS, H);
+    const float *plane = src + ((size_t)f * C + c) * h * w;
+    float *out = dst + ((size_t)f * C + c) * (size_t)H * W;
+    const int f_lo = clip_idx(g.yofs[y_a], h), f_hi = clip_idx(g.yofs[y_b - 1] + 1, h), nfr = f_hi - f_lo + 1;
+    for (int t = threadIdx.x; t < nfr * W; t += blockDim.x) {
+        const int fr = t / W, x = t - fr * W;
+        const float *S0 = plane + (f_lo + fr) * w;
+        const int sx = g.xofs[x];
+        smem[t] = x < g.xmax ? __fadd_rn(__fmul_rn(S0[sx], g.alpha[2 * x]), __fmul_rn(S0[sx + 1], g.alpha[2 * x + 1])) : __fmul_rn(S0[sx], 1.f);
+    }
+    __syncthreads();
+    const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if (vec) {
+        const int W4 = W >> 2;
+        for (int t = threadIdx.x; t < (y_b - y_a) * W4; t += blockDim.x) {
+            const int r = t / W4, x4 = t - r * W4, y = y_a + r;
+            const int sy = g.yofs[y];
+            const float b0 = g.beta[2 * y], b1 = g.beta[2 * y + 1];
+            const float4 r0 = reinterpret_cast<const float4 *>(smem + (clip_idx(sy, h) - f_lo) * W)[x4];
+            const float4 r1 = reinterpret_cast<const float4 *>(smem + (clip_idx(sy + 1, h) - f_lo) * W)[x4];
+            float4 v;
+            v.x = __fadd_rn(__fmul_rn(r0.x, b0), __fmul_rn(r1.x, b1));
+            v.y = __fadd_rn(__fmul_rn(r0.y, b0), __fmul_rn(r1.y, b1));
+            v.z = __fadd_rn(__fmul_rn(r0.z, b0), __fmul_rn(r1.z, b1));
+            v.w = __fadd_rn(__fmul_rn(r0.w, b0), __fmul_rn(r1.w, b1));
+            __stcs(reinterpret_cast<float4 *>(out + (size_t)y * W) + x4, v);
+        }
+    } else {
+        for (int t = threadIdx.x; t < (y_b - y_a) * W; t += blockDim.x) {
+            const int r = t / W, x = t - r * W, y = y_a + r;
+            const int sy = g.yofs[y];
+            const float r0 = smem[(clip_idx(sy, h) - f_lo) * W + x], r1 = smem[(clip_idx(sy + 1, h) - f_lo) * W + x];
+            __stcs(out + (size_t)y * W + x, __fadd_rn(__fmul_rn(r0, g.beta[2 * y]), __fmul_rn(r1, g.beta[2 * y + 1])));
+        }
+    }
+}
+
 // Latency-mode ingest: a few frames in pinned host memory are pulled over PCIe by the SMs (wide
 // coalesced loads, every request in flight at once) into the staging buffers, and the frame
 // counters are cleared by the same launch: one kernel instead of a memset and two DMA copies whose
@@ -935,11 +987,114 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
 // ------------------------------------------------------------------------------------------------
 #define G_TX 64
 #define G_TY 32
+
+// Row pass of cv::GaussianBlur's general RowFilter form over a staged region, register-blocked: a thread produces Q
+// neighbouring outputs of one row from a sliding window it keeps in registers (one shared-memory load per tap and Q
+// multiply-adds, instead of one load per multiply-add).  out[r][c] = k[0] in[r][c] + k[1] in[r][c+1] + ... left to
+// right, the same products and sums as the one-output-per-thread form.
+template <bool FIRST, int Q>
+__device__ __forceinline__ void row_chunk(const float *__restrict__ taps, int j0, int K, float (&win)[2 * Q], float (&acc)[Q])
+{
+#pragma unroll
+    for (int jj = 0; jj < Q; ++jj) {
+        if (j0 + jj < K) {
+            const float t = taps[j0 + jj];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float pr = __fmul_rn(t, win[jj + q]);
+                acc[q] = (FIRST && jj == 0) ? pr : __fadd_rn(acc[q], pr);
+            }
+        }
+    }
+}
+
+// Rows [r_a, r_b] and output columns [c_a, c_b] only (the part of the tile near values above the skip threshold).
+__device__ __forceinline__ void row_pass_blocked(const float *in, int IWs, float *out, int OW, const float *__restrict__ taps, int K, int r_a, int r_b,
+                                                 int c_a, int c_b)
+{
+    constexpr int Q = 7;
+    const int nblk = (c_b - c_a + Q) / Q, rows = r_b - r_a + 1;
+    for (int it = threadIdx.x; it < rows * nblk; it += blockDim.x) {
+        const int r = r_a + it / nblk, c0 = c_a + (it % nblk) * Q;
+        const float *src = in + r * IWs + c0;
+        const int lim = IWs - c0; // entries of this row from src on (the last block reads past the outputs it keeps)
+        float win[2 * Q], acc[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) win[q] = q < lim ? src[q] : 0.f, acc[q] = 0.f;
+        for (int j0 = 0; j0 < K; j0 += Q) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) win[Q + q] = j0 + Q + q < lim ? src[j0 + Q + q] : 0.f;
+            if (j0 == 0) row_chunk<true, Q>(taps, j0, K, win, acc);
+            else row_chunk<false, Q>(taps, j0, K, win, acc);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) win[q] = win[Q + q];
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+            if (c0 + q <= c_b) out[r * OW + c0 + q] = acc[q];
+    }
+}
+
+// Column pass (SymmColumnFilter: s = k[R] x[0]; s += k[R+j] (x[+j] + x[-j]), j = 1..R) for QR rows of one column per
+// thread: the windows of rows above and below slide through registers (two loads per tap for QR outputs).
+// x[i] = tmp[(i) * TW + c]; output row r reads tmp rows r .. r + 2R (its centre is row r + R).
+template <int QR>
+__device__ __forceinline__ void col_pass_blocked(const float *tmp, int TW, int OR, float *out, const float *__restrict__ taps, int R, int y_first,
+                                                 int x_first, int H, int W, int r_a, int r_b, int c_a, int c_b)
+{
+    const float NINF = -CUDART_INF_F;
+    const int nblk = (r_b - r_a + QR) / QR, ncols = c_b - c_a + 1;
+    for (int it = threadIdx.x; it < ncols * nblk; it += blockDim.x) {
+        const int blk = it / ncols, c = c_a + (it - blk * ncols), r0 = r_a + blk * QR;
+        const float *col = tmp + c;
+        const int last = OR + 2 * R - 1; // last row of tmp
+        auto X = [&](int i) { return col[min(i, last) * TW]; }; // rows past the end feed outputs that are dropped
+        float up[QR], dn[QR], sacc[QR];
+        const float tR = taps[R];
+#pragma unroll
+        for (int q = 0; q < QR; ++q) {
+            const float ctr = X(r0 + R + q);
+            up[q] = dn[q] = ctr, sacc[q] = __fmul_rn(tR, ctr);
+        }
+        for (int j0 = 1; j0 <= R; j0 += QR) {
+#pragma unroll
+            for (int jj = 0; jj < QR; ++jj) {
+                const int j = j0 + jj;
+                if (j <= R) {
+                    // after this step the up window holds x[r0+R+q+j], the down window x[r0+R+q-j]; logical entry q lives in
+                    // ring slot (q + jj + 1) % QR resp. (q - jj - 1) mod QR, back in place after QR steps
+                    up[jj % QR] = X(r0 + R + QR - 1 + j);
+                    dn[(QR - 1 - jj) % QR] = X(r0 + R - j);
+                    const float t = taps[R + j];
+#pragma unroll
+                    for (int q = 0; q < QR; ++q) {
+                        const float u = up[(q + jj + 1) % QR], d = dn[((q - jj - 1) % QR + QR) % QR];
+                        sacc[q] = __fadd_rn(sacc[q], __fmul_rn(t, __fadd_rn(u, d)));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < QR; ++q) {
+            const int r = r0 + q;
+            if (r <= r_b) {
+                const int y = y_first + r, x = x_first + c;
+                out[r * TW + c] = (y >= 0 && y < H && x >= 0 && x < W) ? sacc[q] : NINF;
+            }
+        }
+    }
+}
+
+// Any scale (cv::resize INTER_AREA up-sampling = 2-tap linear with area-mode coefficients, src/post-process.h:24-49) and
+// any kernel size: the tile of the up-sampled heat map (+ NMS and filter halo) is built in shared memory straight from
+// the FEATURE map - horizontal 2-tap pass on the feature rows under the tile, vertical 2-tap blend per image row: the same
+// float operations cv::resize performs through its row buffers - so no up-sampled map is read from HBM (or, in
+// skeleton-only mode, ever written).  With p.conf_up != nullptr the tile is read from that materialised map instead.
 __global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic(const K2Params p)
 {
     extern __shared__ __align__(16) float smem[];
     const int frame = blockIdx.z, part = blockIdx.y;
-    const int H = p.g.H, W = p.g.W, K = p.g.K, R = p.g.R;
+    const int H = p.g.H, W = p.g.W, K = p.g.K, R = p.g.R, h = p.g.h, w = p.g.w;
     const int tiles_x = (W + G_TX - 1) / G_TX;
     const int x0 = (blockIdx.x % tiles_x) * G_TX, y0 = (blockIdx.x / tiles_x) * G_TY;
     const int IW = G_TX + 2 + 2 * R, IH = G_TY + 2 + 2 * R; // input region: outputs + NMS halo + filter halo
@@ -947,55 +1102,110 @@ __global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic(const K2Params p
     float *in = smem;           // [IH][IW]
     float *tmp = in + IH * IW;  // [IH][TW]  row-pass result
     float *sm = tmp + IH * TW;  // [G_TY+2][TW] smoothed
-    const float *plane = p.conf_up + ((size_t)frame * OPP_N_HEAT + part) * H * W;
+    float *T = tmp;             // [nfr][IW] horizontally resized feature rows (dead before tmp is written)
     // Only pixels inside the image are smoothed; the filter halo reflects, the NMS halo outside the
     // image is -inf.  Indices of halo pixels whose centre is outside the image are reflected too
     // (harmless: those smoothed values are discarded).
-    int hot = 0;
-    for (int t = threadIdx.x; t < IH * IW; t += blockDim.x) {
-        const int yy = y0 - 1 - R + t / IW, xx = x0 - 1 - R + t % IW;
-        int ry = reflect101(yy, H), rx = reflect101(xx, W);
-        ry = clip_idx(ry, H), rx = clip_idx(rx, W);
-        float v = __ldcg(plane + (size_t)ry * W + rx);
-        // Python-path variant: 'SAME' zero padding of tf.nn.depthwise_conv2d (post_process.py:25-26)
-        if (p.border_zero && (yy < 0 || yy >= H || xx < 0 || xx >= W)) v = 0.f;
-        in[t] = v;
-        hot |= v > p.skip_thresh;
-    }
-    // Same exact early-out as the fast kernel: the staged region is everything the tile's smoothed
-    // pixels depend on; if all of it is <= thresh * (1 - 2^-13) no pixel of the tile can be a peak.
-    if (!__syncthreads_or(hot)) {
-        return;
-    }
-    for (int t = threadIdx.x; t < IH * TW; t += blockDim.x) {
-        const int r = t / TW, c = t % TW;      // output column x0-1+c, centred at in[r][c+R]
-        const float *q = in + r * IW + c;      // q[j] = tap j
-        // reflect relative to the *centre* pixel: taps were staged by absolute reflected index, which
-        // is what REFLECT_101 means for an in-image centre.
-        float s;
-        if (K == 3 && !p.border_zero) {
-            s = __fadd_rn(__fmul_rn(q[R], p.taps[R]), __fmul_rn(__fadd_rn(q[R - 1], q[R + 1]), p.taps[R + 1]));
-        } else if (K == 5 && !p.border_zero) {
-            s = __fadd_rn(__fmul_rn(q[R], p.taps[R]), __fmul_rn(__fadd_rn(q[R - 1], q[R + 1]), p.taps[R + 1]));
-            s = __fadd_rn(s, __fmul_rn(__fadd_rn(q[R - 2], q[R + 2]), p.taps[R + 2]));
-        } else {
-            s = __fmul_rn(p.taps[0], q[0]);
-            for (int j = 1; j < K; ++j) s = __fadd_rn(s, __fmul_rn(p.taps[j], q[j]));
+    // rows [r_a, r_b] x columns [c_a, c_b] of the smoothed tile (sm coordinates: row r is image row y0 - 1 + r) are computed;
+    // the rest of it stands as -inf
+    int r_a = 0, r_b = G_TY + 1, c_a = 0, c_b = TW - 1;
+    if (p.conf_up) {
+        int hot = 0;
+        const float *plane = p.conf_up + ((size_t)frame * OPP_N_HEAT + part) * H * W;
+        for (int t = threadIdx.x; t < IH * IW; t += blockDim.x) {
+            const int yy = y0 - 1 - R + t / IW, xx = x0 - 1 - R + t % IW;
+            int ry = reflect101(yy, H), rx = reflect101(xx, W);
+            ry = clip_idx(ry, H), rx = clip_idx(rx, W);
+            float v = __ldcg(plane + (size_t)ry * W + rx);
+            // Python-path variant: 'SAME' zero padding of tf.nn.depthwise_conv2d (post_process.py:25-26)
+            if (p.border_zero && (yy < 0 || yy >= H || xx < 0 || xx >= W)) v = 0.f;
+            in[t] = v;
+            hot |= v > p.skip_thresh;
         }
-        tmp[t] = s;
+        // Same exact early-out as the fast kernel: the staged region is everything the tile's smoothed
+        // pixels depend on; if all of it is <= thresh * (1 - 2^-13) no pixel of the tile can be a peak.
+        if (!__syncthreads_or(hot)) return;
+    } else {
+        const float *plane = p.conf + ((size_t)frame * OPP_N_HEAT + part) * h * w;
+        // image rows the tile's in-image pixels can reach, and the feature rows under them
+        const int ylo = max(y0 - 1 - R, 0), yhi = min(y0 + G_TY + R, H - 1);
+        const int f_lo = clip_idx(p.g.yofs[ylo], h), f_hi = clip_idx(p.g.yofs[yhi] + 1, h);
+        const int nfr = f_hi - f_lo + 1;
+        {
+            // Which part of the tile can hold a peak at all?  Every pixel of the up-sampled map is a blend, with non-negative
+            // weights that sum to 1 within 2^-23 per pass, of the (at most) 2 x 2 feature cells under it: pixels all of whose
+            // cells are <= thresh (1 - 2^-13) stay below that bound within 2^-21, smooth to <= thresh, cannot be peaks and
+            // cannot outrank one.  The bounding box of the pixels that cells ABOVE the bound can reach, grown by the filter
+            // radius, is the only part of the tile worth smoothing; a tile with no such cell is done.
+            __shared__ int s_bb[4];
+            if (threadIdx.x == 0) s_bb[0] = s_bb[2] = 0x7fffffff, s_bb[1] = s_bb[3] = -1;
+            __syncthreads();
+            const int xlo = max(x0 - 1 - R, 0), xhi = min(x0 + G_TX + R, W - 1);
+            const int c_lo = clip_idx(p.g.xofs[xlo], w), c_hi = clip_idx(p.g.xofs[xhi] + 1, w), ncf = c_hi - c_lo + 1;
+            for (int t = threadIdx.x; t < nfr * ncf; t += blockDim.x) {
+                const int fr = f_lo + t / ncf, fc = c_lo + t % ncf;
+                if (plane[fr * w + fc] > p.skip_thresh) {
+                    // pixels whose two taps include this cell: source index fr - 1 or fr, i.e. y h / H in [fr - 1, fr + 1);
+                    // one pixel of slack on either side for the rounding of cv::resize's double-precision scale
+                    const int ya = (int)(((long)(fr - 1) * H) / h) - 1, yb = (int)(((long)(fr + 1) * H + h - 1) / h) + 1;
+                    const int xa = (int)(((long)(fc - 1) * W) / w) - 1, xb = (int)(((long)(fc + 1) * W + w - 1) / w) + 1;
+                    atomicMin(&s_bb[0], ya), atomicMax(&s_bb[1], yb), atomicMin(&s_bb[2], xa), atomicMax(&s_bb[3], xb);
+                }
+            }
+            __syncthreads();
+            if (s_bb[1] < 0) return;
+            r_a = max(s_bb[0] - R - (y0 - 1), 0), r_b = min(s_bb[1] + R - (y0 - 1), G_TY + 1);
+            c_a = max(s_bb[2] - R - (x0 - 1), 0), c_b = min(s_bb[3] + R - (x0 - 1), TW - 1);
+            if (r_a > r_b || c_a > c_b) return;
+        }
+        // region rows r_a .. r_b + 2R and region columns c_a .. c_b + 2R are what the two passes read
+        const int t_a = c_a, t_n = c_b + 2 * R - c_a + 1;
+        for (int t = threadIdx.x; t < nfr * t_n; t += blockDim.x) {
+            const int fr = t / t_n, tc = t_a + (t - fr * t_n), xx = x0 - 1 - R + tc;
+            const int rx = clip_idx(reflect101(xx, W), W);
+            const float *S0 = plane + (f_lo + fr) * w;
+            const int sx = p.g.xofs[rx];
+            float v;
+            if (rx < p.g.xmax) v = __fadd_rn(__fmul_rn(S0[sx], p.g.alpha[2 * rx]), __fmul_rn(S0[sx + 1], p.g.alpha[2 * rx + 1]));
+            else v = __fmul_rn(S0[sx], 1.f);
+            T[fr * IW + tc] = v;
+        }
+        __syncthreads();
+        // vertical blend: a warp per region row (row index, source rows and coefficients once per row), lanes across it
+        for (int i = r_a + (threadIdx.x >> 5); i <= r_b + 2 * R; i += blockDim.x >> 5) {
+            const int yy = y0 - 1 - R + i;
+            const bool row_out = yy < 0 || yy >= H;
+            const int ry = min(max(clip_idx(reflect101(yy, H), H), ylo), yhi); // rows beyond feed dropped outputs only
+            const int sy = p.g.yofs[ry];
+            const float *T0 = T + (clip_idx(sy, h) - f_lo) * IW, *T1 = T + (clip_idx(sy + 1, h) - f_lo) * IW;
+            const float b0 = p.g.beta[2 * ry], b1 = p.g.beta[2 * ry + 1];
+            for (int tc = t_a + (threadIdx.x & 31); tc < t_a + t_n; tc += 32) {
+                const int xx = x0 - 1 - R + tc;
+                float v = __fadd_rn(__fmul_rn(T0[tc], b0), __fmul_rn(T1[tc], b1));
+                if (p.border_zero && (row_out || xx < 0 || xx >= W)) v = 0.f;
+                in[i * IW + tc] = v;
+            }
+        }
+        __syncthreads();
+    }
+    const float NINF_ = -CUDART_INF_F;
+    const bool whole = r_a == 0 && r_b == G_TY + 1 && c_a == 0 && c_b == TW - 1;
+    if (!whole)
+        for (int t = threadIdx.x; t < (G_TY + 2) * TW; t += blockDim.x) sm[t] = NINF_;
+    if ((K == 3 || K == 5) && !p.border_zero) { // OpenCV's symmetric-small row forms
+        const int ncols = c_b - c_a + 1;
+        for (int t = threadIdx.x; t < (r_b + 2 * R - r_a + 1) * ncols; t += blockDim.x) {
+            const int r = r_a + t / ncols, c = c_a + t % ncols;
+            const float *q = in + r * IW + c;
+            float sv = __fadd_rn(__fmul_rn(q[R], p.taps[R]), __fmul_rn(__fadd_rn(q[R - 1], q[R + 1]), p.taps[R + 1]));
+            if (K == 5) sv = __fadd_rn(sv, __fmul_rn(__fadd_rn(q[R - 2], q[R + 2]), p.taps[R + 2]));
+            tmp[r * TW + c] = sv;
+        }
+    } else {
+        row_pass_blocked(in, IW, tmp, TW, p.taps, K, r_a, r_b + 2 * R, c_a, c_b);
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < (G_TY + 2) * TW; t += blockDim.x) {
-        const int r = t / TW, c = t % TW;
-        const int y = y0 - 1 + r, x = x0 - 1 + c;
-        float s = -CUDART_INF_F;
-        if (y >= 0 && y < H && x >= 0 && x < W) {
-            const float *q = tmp + (r + R) * TW + c;
-            s = __fmul_rn(p.taps[R], q[0]);
-            for (int j = 1; j <= R; ++j) s = __fadd_rn(s, __fmul_rn(p.taps[R + j], __fadd_rn(q[j * TW], q[-j * TW])));
-        }
-        sm[t] = s;
-    }
+    col_pass_blocked<6>(tmp, TW, G_TY + 2, sm, p.taps, R, y0 - 1, x0 - 1, H, W, r_a, r_b, c_a, c_b);
     __syncthreads();
     for (int t = threadIdx.x; t < G_TY * G_TX; t += blockDim.x) {
         const int r = t / G_TX, c = t % G_TX;
@@ -2469,7 +2679,13 @@ cudaError_t launch_k2_generic(const K2Params &p, int n_frames, cudaStream_t st)
 {
     const int R = p.g.R;
     const int IW = G_TX + 2 + 2 * R, IH = G_TY + 2 + 2 * R, TW = G_TX + 2;
-    size_t smem = ((size_t)IH * IW + (size_t)IH * TW + (size_t)(G_TY + 2) * TW) * sizeof(float);
+    // feature rows under the IH image rows of a region (+ the second tap's row, + rounding): they are resized
+    // horizontally into the bytes the row-pass result and the smoothed tile use afterwards
+    long nfr = ((long)IH * p.g.h + p.g.H - 1) / p.g.H + 3;
+    if (nfr > p.g.h) nfr = p.g.h;
+    size_t after_in = (size_t)IH * TW + (size_t)(G_TY + 2) * TW;
+    if ((size_t)nfr * IW > after_in) after_in = (size_t)nfr * IW;
+    size_t smem = ((size_t)IH * IW + after_in) * sizeof(float);
     if ((size_t)OPP_N_PARTS * p.capP * sizeof(int) > smem) smem = (size_t)OPP_N_PARTS * p.capP * sizeof(int);
     int dyn_limit = 0;
     BIG_SMEM_LIMIT(k2_peaks_generic, dyn_limit);
@@ -2557,6 +2773,17 @@ cudaError_t launch_k1(const K1Params &p, cudaStream_t st)
         dim3 grid((g.h + rows - 1) / rows, p.C + p.C2, p.n);
         k1_replicate_chw<8><<<grid, OPP_THREADS, rows * g.w * sizeof(float), st>>>(p, rows);
         return cudaGetLastError();
+    }
+    if (p.layout == OPP_LAYOUT_CHW && g.S <= 0 && g.xofs) { // non-integer scale, channels-first: row-buffer form
+        const long nfr_max = std::min<long>(g.h, ((long)K1G_ROWS * g.h + g.H - 1) / g.H + 3);
+        const size_t smem = (size_t)nfr_max * g.W * sizeof(float);
+        int dyn_limit = 0;
+        BIG_SMEM_LIMIT(k1_general_chw, dyn_limit);
+        if (smem <= (size_t)dyn_limit) {
+            dim3 grid((g.H + K1G_ROWS - 1) / K1G_ROWS, p.C + p.C2, p.n);
+            k1_general_chw<<<grid, OPP_THREADS, smem, st>>>(p);
+            return cudaGetLastError();
+        }
     }
     K1Params q = p;
     for (int part = 0; part < 2; ++part) {

@@ -61,6 +61,26 @@ def test_generic_kernel_sizes_and_scales(mods):
         H.run_and_check(eng, orc, conf, paf, "generic %dx%d k=%d" % (oh, ow, k))
 
 
+def test_non_integer_scales_from_feature_maps_and_from_the_materialised_map(mods, monkeypatch):
+    """Non-integer scales: the generic peak kernel builds its tiles from the feature maps (horizontal 2-tap pass on the
+    feature rows, vertical blend per image row = cv::resize's own operations) or, with OPP_GENERIC_VIA_MAP=1, reads a
+    materialised map: both bit-exact against the oracle.  Large kernels, both border rules, odd sizes, noisy maps that
+    reach every border, and scales close to 1 (where nearly every feature row is its own image row)."""
+    Engine, Oracle, H = mods
+    from openpose_plus_b200 import _capi as capi
+    rng = np.random.default_rng(21)
+    conf, paf = synth.render_batch(2, n_people=6, seed0=930)
+    conf[:, :18] = np.maximum(conf[:, :18], (0.5 * rng.random((2, 18, 46, 54), dtype=np.float32) ** 6).astype(np.float32))
+    for via_map in ("0", "1"):
+        monkeypatch.setenv("OPP_GENERIC_VIA_MAP", via_map)
+        for (oh, ow, k, variant) in [(300, 400, 17, 0), (369, 433, 9, 0), (47, 55, 3, 0), (60, 70, 5, 0), (97, 100, 13, 0), (300, 400, 25, 1),
+                                     (333, 431, 31, 0), (200, 433, 41, 0), (368, 433, 17, 0), (150, 150, 7, 1)]:
+            eng = Engine(46, 54, oh, ow, gauss_kernel_size=k, max_batch=2, max_peaks_per_part=1024, max_cands_per_limb=4096, max_humans=512, variant=variant)
+            assert eng.peak_kernel() == "generic"
+            H.run_and_check(eng, Oracle(46, 54, oh, ow, k, variant=variant), conf, paf, "generic %dx%d k=%d variant %d via_map=%s" % (oh, ow, k, variant, via_map))
+            eng.close()
+
+
 def test_values_around_the_peak_threshold(mods):
     """The peak kernel skips blocks that provably stay below THRESH_HEAT; maps whose smoothed maxima sit
     just below / just above 0.05, flat backgrounds near it, and isolated spikes must still be bit-exact."""
