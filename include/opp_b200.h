@@ -167,6 +167,12 @@ float opp_last_batch_ms(opp_handle_t h, int ticket);
 int opp_device(opp_handle_t h);
 /* Number of kernel launches issued by this handle so far. */
 int64_t opp_launch_count(opp_handle_t h);
+/* Memory-safety check (debug builds only).  A library built with -DOPP_DEBUG_BOUNDS (python -m openpose_plus_b200.build
+ * --debug -> libopp_b200_dbg.so) checks every access to the arrays its kernels carve out of shared memory; this call waits
+ * for the device, returns the first violation since the last call as out = {source line of the array in
+ * csrc/opp_kernels.cu, index, size, number of violations} (all 0: none) and clears the record.  OPP_ERR_INVALID in a
+ * release build. */
+int opp_debug_bounds_report(opp_handle_t h, int32_t out[4]);
 /* Which peak kernel opp_create selected for this geometry and kernel size (a static string):
  *   "fast"        integer scale 8 or 4, Gaussian radius <= 2 x scale (k <= 33 at x8): reads the feature maps only
  *   "generic_rep" any other integer scale / larger kernels: replication-aware, reads the feature maps only

@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libopp_b200.so")
+# OPP_B200_LIB selects another build of the same library (e.g. libopp_b200_dbg.so, the bounds-checked one)
+LIB_PATH = os.environ.get("OPP_B200_LIB") or os.path.join(HERE, "libopp_b200.so")
 
 N_PARTS, N_PAIRS, N_HEAT, N_PAF = 18, 19, 19, 38
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -102,7 +103,7 @@ def lib():
 
 
 EXPORTS = ["opp_config_default", "opp_create", "opp_destroy", "opp_process", "opp_submit", "opp_wait",
-           "opp_last_batch_ms", "opp_launch_count", "opp_peak_kernel", "opp_device", "opp_host_alloc", "opp_host_free", "opp_host_alloc_ex",
+           "opp_last_batch_ms", "opp_launch_count", "opp_peak_kernel", "opp_debug_bounds_report", "opp_device", "opp_host_alloc", "opp_host_free", "opp_host_alloc_ex",
            "opp_host_register", "opp_host_unregister", "opp_stream_wait_ticket", "opp_debug_fetch",
            "opp_resize_device", "opp_resize_pair_device", "opp_peaks_device", "opp_timer_start", "opp_timer_stop", "opp_last_error", "opp_version", "opp_draw_human", "opp_bench_latency", "opp_bench_h2d", "process_conf_paf"]
 

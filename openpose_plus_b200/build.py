@@ -37,6 +37,21 @@ def build(force=False, verbose=False):
     return OUT
 
 
+OUT_DEBUG = os.path.join(HERE, "libopp_b200_dbg.so")
+
+
+def build_debug(force=False):
+    """The same library with every shared-memory array access bounds-checked (-DOPP_DEBUG_BOUNDS, csrc/opp_kernels.cu Span):
+    the stand-in for compute-sanitizer, which the GPU pool does not offer.  Load it with OPP_B200_LIB=<path>; the fuzzers in
+    scripts/ report what opp_debug_bounds_report recorded."""
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "opp_b200.h"), __file__]
+    if not force and os.path.exists(OUT_DEBUG) and all(os.path.getmtime(d) <= os.path.getmtime(OUT_DEBUG) for d in deps):
+        return OUT_DEBUG
+    flags = [f for f in FLAGS if f != "-O3"] + ["-O2", "-DOPP_DEBUG_BOUNDS"]
+    subprocess.run([NVCC] + flags + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT_DEBUG], check=True)
+    return OUT_DEBUG
+
+
 CUOBJDUMP = os.path.join(os.path.dirname(NVCC), "cuobjdump")
 
 
@@ -86,4 +101,7 @@ def build_dropin_against_reference_headers(force=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--debug" in sys.argv:
+        print(build_debug(force="--force" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1113,6 +1113,24 @@ int opp_bench_h2d(opp_handle_t h, const float *conf, const float *paf, int n_fra
 
 int64_t opp_launch_count(opp_handle_t h) { return h ? h->launches : 0; }
 
+int opp_debug_bounds_report(opp_handle_t h, int32_t out[4])
+{
+    if (!h || !out) return OPP_ERR_INVALID;
+    DeviceGuard guard_(h->device);
+    int rec[4] = {0, 0, 0, 0};
+    const cudaError_t e = opp_kernels_bounds_report(rec, true);
+    if (e == cudaErrorNotSupported) {
+        set_err(&h->err, "opp_debug_bounds_report: this library was built without -DOPP_DEBUG_BOUNDS");
+        return OPP_ERR_INVALID;
+    }
+    if (e != cudaSuccess) {
+        set_err(&h->err, "opp_debug_bounds_report: %s", cudaGetErrorString(e));
+        return OPP_ERR_CUDA;
+    }
+    for (int i = 0; i < 4; ++i) out[i] = rec[i];
+    return OPP_OK;
+}
+
 const char *opp_peak_kernel(opp_handle_t h)
 {
     if (!h) return "";

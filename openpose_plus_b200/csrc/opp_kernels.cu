@@ -54,6 +54,38 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 
 __device__ __forceinline__ int clip_idx(int v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); }
 
+// Bounds checking for the arrays the kernels carve out of shared memory (and a few global ones).  compute-sanitizer is
+// not available on the GPU pool this is developed on, so the library can be built a second time with -DOPP_DEBUG_BOUNDS
+// (openpose_plus_b200/build.py build_debug -> libopp_b200_dbg.so): every Span access is then checked, the first
+// violation is recorded (source line of the Span's declaration, index, size) and the access is redirected to element 0
+// instead of corrupting memory; opp_debug_bounds_report() reads the record.  In the release build a Span is a bare pointer.
+#ifdef OPP_DEBUG_BOUNDS
+__device__ int g_oob[4]; // line, index, size, number of violations
+__device__ __noinline__ void oob_record(int line, long i, long n)
+{
+    if (atomicAdd(&g_oob[3], 1) == 0) g_oob[0] = line, g_oob[1] = (int)i, g_oob[2] = (int)n;
+}
+template <typename T> struct Span {
+    T *p;
+    long n;
+    int line;
+    __device__ __forceinline__ T &operator[](long i) const
+    {
+        if (i < 0 || i >= n) oob_record(line, i, n), i = 0;
+        return p[i];
+    }
+    __device__ __forceinline__ Span<T> from(long ofs) const { return Span<T>{p + ofs, n - ofs, line}; } // the tail starting at ofs
+};
+#define SPAN(T, ptr, n) Span<T> { (ptr), (long)(n), __LINE__ }
+#else
+template <typename T> struct Span {
+    T *p;
+    __device__ __forceinline__ T &operator[](long i) const { return p[i]; }
+    __device__ __forceinline__ Span<T> from(long ofs) const { return Span<T>{p + ofs}; }
+};
+#define SPAN(T, ptr, n) Span<T> { (ptr) }
+#endif
+
 // Asynchronous global -> shared staging (cp.async / LDGSTS): every thread queues all its pieces
 // before anything waits, so a tile costs one memory round trip instead of one per loop iteration.
 // 16-byte pieces when both sides are 16-byte aligned, 4-byte pieces otherwise.  Completed by
@@ -416,7 +448,7 @@ struct PeakSource {
     const float *conf_up; // materialised [n,19,H,W] map when the geometry has no closed form (non-integer scale)
 };
 
-__device__ __forceinline__ void order_part_peaks(const PeakSource &src, int frame, int part, const int *s_keys, int n, int ofs, int2 *s_xy,
+__device__ __forceinline__ void order_part_peaks(const PeakSource &src, int frame, int part, const Span<int> s_keys, int n, int ofs, const Span<int2> s_xy,
                                                  opp_peak_t *out /* frame's all_peaks, or nullptr: another limb writes this part's slice */)
 {
     const int W = src.g.W, H = src.g.H;
@@ -669,20 +701,20 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
     const int ilo = max(ia - 1 - NB, 0), ihi = min(ib + 1 + NB, h); // halo row + its own filter neighbours
     const int nr = ihi - ilo, ncol = jhi - jlo;
     const int RW = S * ncol;
-    float *L = smem;                          // [nr][w] feature rows
-    float *Rrow = smem + ((nr * w + 3) & ~3); // [nr][RW] row-pass result
-    float *Pf = Rrow + ((nr * RW + 3) & ~3);  // [2][ib-ia][w] PAF feature rows of the tile (STORE only)
+    const Span<float> L = SPAN(float, smem, nr * w);                                       // [nr][w] feature rows
+    const Span<float> Rrow = SPAN(float, smem + ((nr * w + 3) & ~3), nr * RW);             // [nr][RW] row-pass result
+    const Span<float> Pf = SPAN(float, Rrow.p + ((nr * RW + 3) & ~3), 2 * (ib - ia) * w);  // [2][ib-ia][w] PAF feature rows of the tile (STORE only)
     const float *src = p.conf + ((size_t)frame * OPP_N_HEAT + part) * h * w + ilo * w;
     pdl_trigger(); // the limb kernel may be scheduled behind this grid at once (it can fetch PAF tiles from pinned memory
                    // meanwhile); it waits for our completion itself before touching the peaks
     pdl_wait();    // the maps (and the counters) may come from an ingest kernel still in flight
-    stage_async(L, src, nr * w);
+    stage_async(L.p, src, nr * w);
     if (STORE) {
         // staged up front: a load issued next to the store stream would queue behind it for microseconds
         const int nt = (ib - ia) * w;
         const float *ps = p.paf + (((size_t)frame * OPP_N_PAF + 2 * part) * h + ia) * w;
-        stage_async(Pf, ps, nt);
-        stage_async(Pf + nt, ps + (size_t)h * w, nt);
+        stage_async(Pf.p, ps, nt);
+        stage_async(Pf.p + nt, ps + (size_t)h * w, nt);
     }
     stage_wait();
     __syncthreads();
@@ -800,7 +832,7 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
         for (int it = threadIdx.x; it < nr * ncol; it += blockDim.x) {
             const int r = it / ncol, c = jlo + (it - r * ncol);
             if (!((s_need[r] >> (c - jlo)) & 1ull)) continue; // no active block reads this cell
-            const float *Lr = L + r * w;
+            const Span<float> Lr = L.from(r * w);
             float out[S];
             const float m2 = NB > 1 ? Lr[max(c - 2, 0)] : 0.f, m1 = Lr[max(c - 1, 0)], p1 = Lr[min(c + 1, w - 1)], p2 = NB > 1 ? Lr[min(c + 2, w - 1)] : 0.f;
             constexpr bool kRowPacked = R > 2 || BZ; // the symmetric-small forms (k = 3, 5) stay as OpenCV writes them
@@ -813,7 +845,7 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
                 if (kRowPacked) row_taps2<S, R>(p.taps, win, out);
                 else row_taps<S, R, BZ>(p.taps, win, out);
             }
-            float *d = Rrow + r * RW + S * (c - jlo);
+            float *d = &Rrow[r * RW + S * (c - jlo)];
             if (S % 4 == 0) {
 #pragma unroll
                 for (int q = 0; q < S; q += 4) *reinterpret_cast<float4 *>(d + q) = make_float4(out[q], out[q + 1], out[q + 2], out[q + 3]);
@@ -842,7 +874,7 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
         const bool have0 = x0 >= xlo && x0 < xhi, have1 = x1 >= xlo && x1 < xhi;
         const float thr0 = (lane >= 1 && x0 < X1) ? p.thresh : CUDART_INF_F;
         const float thr1 = (lane <= 30 && x1 < X1) ? p.thresh : CUDART_INF_F;
-        const float *col0 = Rrow + (have0 ? x0 - xlo : 0), *col1 = Rrow + (have1 ? x1 - xlo : 0);
+        const Span<float> col0 = Rrow.from(have0 ? x0 - xlo : 0), col1 = Rrow.from(have1 ? x1 - xlo : 0);
         NmsState n0 = {NINF, NINF, NINF}, n1 = {NINF, NINF, NINF};
 
         // one finished image row: decide the row above it.  Decisions are collected as bit masks (bit =
@@ -1009,14 +1041,14 @@ __device__ __forceinline__ void row_chunk(const float *__restrict__ taps, int j0
 }
 
 // Rows [r_a, r_b] and output columns [c_a, c_b] only (the part of the tile near values above the skip threshold).
-__device__ __forceinline__ void row_pass_blocked(const float *in, int IWs, float *out, int OW, const float *__restrict__ taps, int K, int r_a, int r_b,
+__device__ __forceinline__ void row_pass_blocked(const Span<float> in, int IWs, const Span<float> out, int OW, const float *__restrict__ taps, int K, int r_a, int r_b,
                                                  int c_a, int c_b)
 {
     constexpr int Q = 7;
     const int nblk = (c_b - c_a + Q) / Q, rows = r_b - r_a + 1;
     for (int it = threadIdx.x; it < rows * nblk; it += blockDim.x) {
         const int r = r_a + it / nblk, c0 = c_a + (it % nblk) * Q;
-        const float *src = in + r * IWs + c0;
+        const Span<float> src = in.from(r * IWs + c0);
         const int lim = IWs - c0; // entries of this row from src on (the last block reads past the outputs it keeps)
         float win[2 * Q], acc[Q];
 #pragma unroll
@@ -1039,14 +1071,14 @@ __device__ __forceinline__ void row_pass_blocked(const float *in, int IWs, float
 // thread: the windows of rows above and below slide through registers (two loads per tap for QR outputs).
 // x[i] = tmp[(i) * TW + c]; output row r reads tmp rows r .. r + 2R (its centre is row r + R).
 template <int QR>
-__device__ __forceinline__ void col_pass_blocked(const float *tmp, int TW, int OR, float *out, const float *__restrict__ taps, int R, int y_first,
+__device__ __forceinline__ void col_pass_blocked(const Span<float> tmp, int TW, int OR, const Span<float> out, const float *__restrict__ taps, int R, int y_first,
                                                  int x_first, int H, int W, int r_a, int r_b, int c_a, int c_b)
 {
     const float NINF = -CUDART_INF_F;
     const int nblk = (r_b - r_a + QR) / QR, ncols = c_b - c_a + 1;
     for (int it = threadIdx.x; it < ncols * nblk; it += blockDim.x) {
         const int blk = it / ncols, c = c_a + (it - blk * ncols), r0 = r_a + blk * QR;
-        const float *col = tmp + c;
+        const Span<float> col = tmp.from(c);
         const int last = OR + 2 * R - 1; // last row of tmp
         auto X = [&](int i) { return col[min(i, last) * TW]; }; // rows past the end feed outputs that are dropped
         float up[QR], dn[QR], sacc[QR];
@@ -1099,10 +1131,11 @@ __global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic(const K2Params p
     const int x0 = (blockIdx.x % tiles_x) * G_TX, y0 = (blockIdx.x / tiles_x) * G_TY;
     const int IW = G_TX + 2 + 2 * R, IH = G_TY + 2 + 2 * R; // input region: outputs + NMS halo + filter halo
     const int TW = G_TX + 2;
-    float *in = smem;           // [IH][IW]
-    float *tmp = in + IH * IW;  // [IH][TW]  row-pass result
-    float *sm = tmp + IH * TW;  // [G_TY+2][TW] smoothed
-    float *T = tmp;             // [nfr][IW] horizontally resized feature rows (dead before tmp is written)
+    const Span<float> in = SPAN(float, smem, IH * IW);                     // [IH][IW]
+    const Span<float> tmp = SPAN(float, smem + IH * IW, IH * TW);          // [IH][TW]  row-pass result
+    const Span<float> sm = SPAN(float, tmp.p + IH * TW, (G_TY + 2) * TW);  // [G_TY+2][TW] smoothed
+    // [nfr][IW] horizontally resized feature rows (dead before tmp is written; the launcher sizes the bytes behind `in` for it)
+    const Span<float> T = SPAN(float, tmp.p, (size_t)min((long)h, ((long)IH * h + H - 1) / H + 3) * IW);
     // Only pixels inside the image are smoothed; the filter halo reflects, the NMS halo outside the
     // image is -inf.  Indices of halo pixels whose centre is outside the image are reflected too
     // (harmless: those smoothed values are discarded).
@@ -1177,7 +1210,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic(const K2Params p
             const bool row_out = yy < 0 || yy >= H;
             const int ry = min(max(clip_idx(reflect101(yy, H), H), ylo), yhi); // rows beyond feed dropped outputs only
             const int sy = p.g.yofs[ry];
-            const float *T0 = T + (clip_idx(sy, h) - f_lo) * IW, *T1 = T + (clip_idx(sy + 1, h) - f_lo) * IW;
+            const Span<float> T0 = T.from((clip_idx(sy, h) - f_lo) * IW), T1 = T.from((clip_idx(sy + 1, h) - f_lo) * IW);
             const float b0 = p.g.beta[2 * ry], b1 = p.g.beta[2 * ry + 1];
             for (int tc = t_a + (threadIdx.x & 31); tc < t_a + t_n; tc += 32) {
                 const int xx = x0 - 1 - R + tc;
@@ -1196,7 +1229,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic(const K2Params p
         const int ncols = c_b - c_a + 1;
         for (int t = threadIdx.x; t < (r_b + 2 * R - r_a + 1) * ncols; t += blockDim.x) {
             const int r = r_a + t / ncols, c = c_a + t % ncols;
-            const float *q = in + r * IW + c;
+            const Span<float> q = in.from(r * IW + c);
             float sv = __fadd_rn(__fmul_rn(q[R], p.taps[R]), __fmul_rn(__fadd_rn(q[R - 1], q[R + 1]), p.taps[R + 1]));
             if (K == 5) sv = __fadd_rn(sv, __fmul_rn(__fadd_rn(q[R - 2], q[R + 2]), p.taps[R + 2]));
             tmp[r * TW + c] = sv;
@@ -1211,12 +1244,12 @@ __global__ void __launch_bounds__(OPP_THREADS) k2_peaks_generic(const K2Params p
         const int r = t / G_TX, c = t % G_TX;
         const int y = y0 + r, x = x0 + c;
         if (y >= H || x >= W) continue;
-        const float *q = sm + (r + 1) * TW + (c + 1);
-        const float s = q[0];
+        const int o = (r + 1) * TW + (c + 1);
+        const float s = sm[o];
         if (!(s > p.thresh)) continue;
-        float m = fmaxf(fmaxf(q[-TW - 1], q[-TW]), q[-TW + 1]);
-        m = fmaxf(m, fmaxf(fmaxf(q[-1], q[0]), q[1]));
-        m = fmaxf(m, fmaxf(fmaxf(q[TW - 1], q[TW]), q[TW + 1]));
+        float m = fmaxf(fmaxf(sm[o - TW - 1], sm[o - TW]), sm[o - TW + 1]);
+        m = fmaxf(m, fmaxf(fmaxf(sm[o - 1], s), sm[o + 1]));
+        m = fmaxf(m, fmaxf(fmaxf(sm[o + TW - 1], sm[o + TW]), sm[o + TW + 1]));
         if (s == m) emit_peak(p, frame, part, y, x);
     }
 }
@@ -1348,10 +1381,10 @@ struct Cand {
 // crosses empty PAF in the middle: they leave after 4 samples instead of 10 and the survivors (re-evaluated in
 // full, same operations in the same order) fill whole warps.
 struct PairCtx {
-    const float *px, *py; // the limb's x / y PAF planes (feature resolution)
+    Span<const float> px, py; // the limb's x / y PAF planes (feature resolution)
     const OppGeom *g;
-    const float *steps;   // [max(H, W)] d -> (float)d / 10.f (IEEE), or null: the STEP_X / STEP_Y divisions as a table
-    const unsigned *weak; // bit per feature cell: |px| + |py| so small that no sample there can exceed THRESH_VECTOR_SCORE (or null)
+    Span<const float> steps;   // [max(H, W)] d -> (float)d / 10.f (IEEE), or null: the STEP_X / STEP_Y divisions as a table
+    Span<const unsigned> weak; // bit per feature cell: |px| + |py| so small that no sample there can exceed THRESH_VECTOR_SCORE (or null)
     int w, H, sshift;
     float thr;
 };
@@ -1374,8 +1407,8 @@ __device__ __forceinline__ bool pair_may_pass(const PairCtx &c, const int2 A, co
 {
     const int dx = B.x - A.x, dy = B.y - A.y;
     if ((dx | dy) == 0) return false;
-    const float step_x = c.steps ? copysignf(c.steps[abs(dx)], (float)dx) : __fdiv_rn((float)dx, 10.f);
-    const float step_y = c.steps ? copysignf(c.steps[abs(dy)], (float)dy) : __fdiv_rn((float)dy, 10.f);
+    const float step_x = c.steps.p ? copysignf(c.steps[abs(dx)], (float)dx) : __fdiv_rn((float)dx, 10.f);
+    const float step_y = c.steps.p ? copysignf(c.steps[abs(dy)], (float)dy) : __fdiv_rn((float)dy, 10.f);
     const float ax = (float)A.x, ay = (float)A.y;
     int weak = 0;
 #pragma unroll
@@ -1400,8 +1433,8 @@ __device__ __forceinline__ bool score_pair(const PairCtx &c, const int2 A, const
     const float norm = l2 < (1 << 24) ? __fsqrt_rn((float)l2) : (float)sqrt((double)l2);
     const float vx = __fdiv_rn((float)dx, norm), vy = __fdiv_rn((float)dy, norm);
     // STEP_X, STEP_Y = d / 10.f  (:321-322); division rounds symmetrically, so the table of |d| serves both signs
-    const float step_x = c.steps ? copysignf(c.steps[abs(dx)], (float)dx) : __fdiv_rn((float)dx, 10.f);
-    const float step_y = c.steps ? copysignf(c.steps[abs(dy)], (float)dy) : __fdiv_rn((float)dy, 10.f);
+    const float step_x = c.steps.p ? copysignf(c.steps[abs(dx)], (float)dx) : __fdiv_rn((float)dx, 10.f);
+    const float step_y = c.steps.p ? copysignf(c.steps[abs(dy)], (float)dy) : __fdiv_rn((float)dy, 10.f);
     float scores = 0.f;
     int cnt = 0;
 #pragma unroll
@@ -1417,8 +1450,8 @@ __device__ __forceinline__ bool score_pair(const PairCtx &c, const int2 A, const
             const int fi = (ly >> c.sshift) * c.w + (lx >> c.sshift);
             vpx = c.px[fi], vpy = c.py[fi];
         } else {
-            vpx = upsample_at(*c.g, c.px, ly, lx);
-            vpy = upsample_at(*c.g, c.py, ly, lx);
+            vpx = upsample_at(*c.g, c.px.p, ly, lx);
+            vpy = upsample_at(*c.g, c.py.p, ly, lx);
         }
         const float score = __fadd_rn(__fmul_rn(vx, vpx), __fmul_rn(vy, vpy)); // :108-109
         scores = __fadd_rn(scores, score);
@@ -1584,12 +1617,12 @@ __device__ void std_sort_desc(Cand *v, int n)
 //   * a range whose depth budget is spent is heap-sorted sequentially, as libstdc++ does.
 // What remains (__final_insertion_sort) is an insertion sort = the stable order of the array left behind, which the
 // caller produces with a rank sort.  pos_a / pos_b: scratch, n entries each; rng: scratch, 4 (n / 17 + 2) ints.
-__device__ void std_sort_partition_rounds(Cand *v, int n, unsigned short *pos_a, unsigned short *pos_b, int *rng)
+__device__ void std_sort_partition_rounds(const Span<Cand> v, int n, const Span<unsigned short> pos_a, const Span<unsigned short> pos_b, const Span<int> rng)
 {
     __shared__ int s_rcnt[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int max_r = n / 17 + 2;
-    int *rng_lo[2] = {rng, rng + 2 * max_r}; // per level: {first | last << 16, depth}
+    const Span<int> rng_lo[2] = {rng, rng.from(2 * max_r)}; // per level: {first | last << 16, depth}
     if (tid == 0) {
         int lg = 0;
         for (int t = n; t > 1; t >>= 1) ++lg;
@@ -1604,11 +1637,11 @@ __device__ void std_sort_partition_rounds(Cand *v, int n, unsigned short *pos_a,
             const int packed = rng_lo[cur][2 * r], depth = rng_lo[cur][2 * r + 1];
             const int f = packed & 0xffff, l = (packed >> 16) & 0xffff;
             if (depth == 0) {
-                if (lane == 0) heap_sort_range(v + f, v + l);
+                if (lane == 0) heap_sort_range(v.p + f, v.p + l);
                 continue;
             }
             if (lane == 0) { // __move_median_to_first(first, first + 1, mid, last - 1)
-                Cand *first = v + f, *a = first + 1, *b = first + (l - f) / 2, *c = v + l - 1;
+                Cand *first = v.p + f, *a = first + 1, *b = first + (l - f) / 2, *c = v.p + l - 1;
                 if (cand_gt(*a, *b)) {
                     if (cand_gt(*b, *c))
                         cswap(first, b);
@@ -1650,7 +1683,7 @@ __device__ void std_sort_partition_rounds(Cand *v, int n, unsigned short *pos_a,
                 if (mk != 0xffffffffu) break;
             }
             const int cut = K == 0 ? A(0) : ((K < cnt_a && A(K) < B(K - 1)) ? A(K) : B(K - 1));
-            for (int k = lane; k < K; k += 32) cswap(v + A(k), v + B(k));
+            for (int k = lane; k < K; k += 32) cswap(&v[A(k)], &v[B(k)]);
             if (lane == 0) {
                 if (l - cut > 16) {
                     const int i = atomicAdd(&s_rcnt[cur ^ 1], 1);
@@ -1690,10 +1723,10 @@ __device__ __forceinline__ void stamp(const K3Params &p, int frame, int pair_id,
 // without touching global memory, and the output is written by the whole CTA.
 __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem_raw, const int *pofs /* shared: 19 part offsets */)
 {
-    int *hr = reinterpret_cast<int *>(smem_raw + p.off_href);                   // [capH][21]
-    int2 *s_pk = reinterpret_cast<int2 *>(smem_raw + p.off_score);              // [n_peaks] {x | y << 16, score bits} (score_in_smem)
-    opp_conn_t *s_conn = reinterpret_cast<opp_conn_t *>(smem_raw + p.off_conn); // all connections of the frame, or one limb's
-    int *s_keep = reinterpret_cast<int *>(smem_raw + p.off_keep);               // [capH] surviving humans, output order
+    const Span<int> hr = SPAN(int, reinterpret_cast<int *>(smem_raw + p.off_href), p.capH * HR_WORDS);                     // [capH][21]
+    const Span<int2> s_pk = SPAN(int2, reinterpret_cast<int2 *>(smem_raw + p.off_score), p.pk_cap);                          // [n_peaks] {x | y << 16, score bits} (score_in_smem)
+    const Span<opp_conn_t> s_conn = SPAN(opp_conn_t, reinterpret_cast<opp_conn_t *>(smem_raw + p.off_conn), p.conn_cap); // all connections of the frame, or one limb's
+    const Span<int> s_keep = SPAN(int, reinterpret_cast<int *>(smem_raw + p.off_keep), p.capH);                             // [capH] surviving humans, output order
     __shared__ int s_state[8];                                                  // n, -, flags, merges, n_out
     __shared__ int s_nc[OPP_N_PAIRS], s_coff[OPP_N_PAIRS + 1];
     const int capH = p.capH, capP = p.capP;
@@ -1717,9 +1750,9 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
     // Forest form of the 17 tree limbs (see below): s_c1[limb][local index of a first-part peak] = flattened index of
     // the limb's connection that starts at that peak (0xffff: none); s_in = bitmap over peak ids, set when the peak
     // enters a human as the SECOND part of a tree-limb connection; s_lmb[t] = limb of flattened connection t.
-    unsigned short *s_c1 = reinterpret_cast<unsigned short *>(smem_raw + p.off_owner);                                     // [17][capP]
-    unsigned *s_in = reinterpret_cast<unsigned *>(smem_raw + p.off_owner + (((size_t)17 * capP * 2 + 15) & ~(size_t)15)); // [ceil(18 capP / 32)]
-    unsigned char *s_lmb = reinterpret_cast<unsigned char *>(s_in + (((OPP_N_PARTS * capP + 31) / 32 + 3) & ~3));           // [conn_cap]
+    const Span<unsigned short> s_c1 = SPAN(unsigned short, reinterpret_cast<unsigned short *>(smem_raw + p.off_owner), 17 * capP);                               // [17][capP]
+    const Span<unsigned> s_in = SPAN(unsigned, reinterpret_cast<unsigned *>(smem_raw + p.off_owner + (((size_t)17 * capP * 2 + 15) & ~(size_t)15)), (OPP_N_PARTS * capP + 31) / 32); // [ceil(18 capP / 32)]
+    const Span<unsigned char> s_lmb = SPAN(unsigned char, reinterpret_cast<unsigned char *>(s_in.p + (((OPP_N_PARTS * capP + 31) / 32 + 3) & ~3)), p.conn_cap); // [conn_cap]
     __shared__ int s_pofs[OPP_N_PARTS + 1];
     __shared__ int s_nwarp[OPP_THREADS / 32];
     __shared__ unsigned char s_pa[OPP_N_PAIRS], s_pb[OPP_N_PAIRS]; // c_pair_a / c_pair_b for lane-divergent limb indices
@@ -1770,7 +1803,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
         return pk_smem ? __int_as_float(s_pk[id].y) : __ldcg(&peaks[id].score);
     };
     // one limb's connections, in acceptance order; warp 0 only
-    auto do_limb = [&](int pair_id, const opp_conn_t *cl, int nconn, int kstart) {
+    auto do_limb = [&](int pair_id, const Span<opp_conn_t> cl, int nconn, int kstart) {
         const int part1 = c_pair_a[pair_id], part2 = c_pair_b[pair_id];
         for (int k = kstart; k < nconn; ++k) {
             const opp_conn_t conn = cl[k];
@@ -1794,7 +1827,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
                 if (hit0 < 0 || hit0 >= hist_max) {
                     flags |= OPP_FLAG_UB_STALE_INDEX;
                 } else if (lane == 0) {
-                    int *h1 = hr + hit0 * HR_WORDS;
+                    const Span<int> h1 = hr.from(hit0 * HR_WORDS);
                     if (h1[HR_PART + part2] != conn.cid2) {
                         h1[HR_PART + part2] = conn.cid2;
                         h1[HR_NPARTS] += 1;
@@ -1807,7 +1840,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
                 if (hit0 < 0 || hit0 >= hist_max || hit1 < 0 || hit1 >= hist_max) {
                     flags |= OPP_FLAG_UB_STALE_INDEX;
                 } else {
-                    int *h1 = hr + hit0 * HR_WORDS, *h2 = hr + hit1 * HR_WORDS;
+                    const Span<int> h1 = hr.from(hit0 * HR_WORDS), h2 = hr.from(hit1 * HR_WORDS);
                     const bool both = lane < OPP_N_PARTS && h1[HR_PART + lane] > 0 && h2[HR_PART + lane] > 0;
                     const bool membership = __ballot_sync(0xffffffffu, both) != 0;
                     if (!membership) {
@@ -1858,7 +1891,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
                 if (n >= capH) {
                     flags |= OPP_FLAG_HUMAN_OVERFLOW;
                 } else {
-                    int *hn = hr + n * HR_WORDS;
+                    const Span<int> hn = hr.from(n * HR_WORDS);
                     if (lane < OPP_N_PARTS) hn[HR_PART + lane] = lane == part1 ? conn.cid1 : (lane == part2 ? conn.cid2 : -1);
                     if (lane == 0) {
                         hn[HR_ID] = n;
@@ -1890,7 +1923,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
     auto tree_limbs_forest = [&]() {
         const int T = s_coff[17]; // connections of limbs 0..16, flattened in limb order
         int created = 0;          // humans created so far (uniform over the CTA)
-        int *s_create = s_keep;   // [capH] creating connection of each human (s_keep is not in use yet)
+        const Span<int> s_create = s_keep;   // [capH] creating connection of each human (s_keep is not in use yet)
         const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         int tflags = 0;
         auto pscore = [&](int id) -> float {
@@ -1935,7 +1968,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
                 const int pos = before + __popc(m & ((1u << lane) - 1));
                 if (pos < capH) { // part ids were preset to -1 by the whole CTA
                     s_create[pos] = t;
-                    int *hq = hr + pos * HR_WORDS;
+                    const Span<int> hq = hr.from(pos * HR_WORDS);
                     hq[HR_ID] = pos;
                     hq[HR_PART + s_pa[l]] = c.cid1, hq[HR_PART + s_pb[l]] = c.cid2;
                 }
@@ -1957,7 +1990,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
         for (int round = 0; round < 3; ++round) {
             for (int it = threadIdx.x; it < created * 17; it += blockDim.x) {
                 const int q = it / 17, l = it - q * 17;
-                int *hq = hr + q * HR_WORDS + HR_PART;
+                const Span<int> hq = hr.from(q * HR_WORDS + HR_PART);
                 const int pa = s_pa[l], pb = s_pb[l];
                 const int held = hq[pa];
                 if (held < 0 || hq[pb] != -1) continue;
@@ -1972,7 +2005,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
         // later limb in limb order, each as (s(cid2) + conn.score) (:205-209).  The lookups of different limbs are
         // independent now; only the additions are a chain.
         for (int q = threadIdx.x; q < created; q += blockDim.x) {
-            int *hq = hr + q * HR_WORDS;
+            const Span<int> hq = hr.from(q * HR_WORDS);
             const int t0 = s_create[q], l0 = s_lmb[t0];
             float sc = s_conn[t0].score;
             int np = 2;
@@ -2003,7 +2036,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
     // what another connection of the same limb touches (peaks are used once per limb).  Anything else (two humans:
     // merge or overwrite; one human holding another peak there) is order dependent: from the first such connection
     // on, the limb continues in the sequential form.  Returns the index to continue from (nconn: all done).
-    auto virtual_limb_prefix = [&](int pair_id, const opp_conn_t *cl, int nconn) -> int {
+    auto virtual_limb_prefix = [&](int pair_id, const Span<opp_conn_t> cl, int nconn) -> int {
         const int part1 = c_pair_a[pair_id], part2 = c_pair_b[pair_id];
         for (int base = 0; base < nconn; base += 32) {
             const int k = base + lane;
@@ -2014,7 +2047,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
             int nh = 0, h0 = 0;
             if (on)
                 for (int q = 0; q < n; ++q) {
-                    const int *hq = hr + q * HR_WORDS + HR_PART;
+                    const Span<int> hq = hr.from(q * HR_WORDS + HR_PART);
                     if (hq[part1] == conn.cid1 || hq[part2] == conn.cid2) {
                         if (nh == 0) h0 = q;
                         ++nh;
@@ -2026,7 +2059,7 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
             const unsigned mh = __ballot_sync(0xffffffffu, !noop && !safe);
             const int lim = mh ? __ffs(mh) - 1 : 32;
             if (safe && lane < lim) {
-                int *h1 = hr + h0 * HR_WORDS;
+                const Span<int> h1 = hr.from(h0 * HR_WORDS);
                 h1[HR_PART + part2] = conn.cid2;
                 h1[HR_NPARTS] += 1;
                 const float sc = __int_as_float(h1[HR_SCORE]);
@@ -2047,10 +2080,10 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
             for (int pair_id = use_owner ? 17 : 0; pair_id < OPP_N_PAIRS; ++pair_id) {
                 int k0 = 0;
                 if (pair_id >= 17 && merges == 0) {
-                    k0 = virtual_limb_prefix(pair_id, s_conn + s_coff[pair_id], s_nc[pair_id]);
+                    k0 = virtual_limb_prefix(pair_id, s_conn.from(s_coff[pair_id]), s_nc[pair_id]);
                     for (int o = 16; o > 0; o >>= 1) flags |= __shfl_xor_sync(0xffffffffu, flags, o); // lanes set UB flags on their own
                 }
-                do_limb(pair_id, s_conn + s_coff[pair_id], s_nc[pair_id], k0);
+                do_limb(pair_id, s_conn.from(s_coff[pair_id]), s_nc[pair_id], k0);
             }
     } else { // capacities too large to stage every limb at once: one limb at a time
         for (int pair_id = 0; pair_id < OPP_N_PAIRS; ++pair_id) {
@@ -2165,7 +2198,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
     pdl_wait(); // peaks come from the peak kernel, which may still be running when this CTA is scheduled
     // The two key lists of this limb are fetched whole (capP entries each; those beyond the list's size are ignored)
     // in the same round trip as the list sizes, instead of after them.
-    int *s_ka = reinterpret_cast<int *>(smem_raw + p.off_keys), *s_kb = s_ka + capP;
+    const Span<int> s_ka = SPAN(int, reinterpret_cast<int *>(smem_raw + p.off_keys), 2 * capP), s_kb = s_ka.from(capP);
     for (int t = tid; t < 2 * capP; t += blockDim.x) {
         const int part = t < capP ? pa : pb, k = t < capP ? t : t - capP;
         s_ka[t] = __ldcg(p.pk_key + ((size_t)frame * OPP_N_PARTS + part) * capP + k);
@@ -2190,18 +2223,19 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
     const int ofs_b = s_pofs3[pb], nb = s_pcnt[pb];
     opp_peak_t *peaks = p.peaks + (size_t)frame * OPP_N_PARTS * capP;
 
-    int2 *s_pa = reinterpret_cast<int2 *>(smem_raw + p.off_pk);          // [capP]
-    int2 *s_pb = s_pa + capP;                                            // [capP]
-    unsigned char *s_used = smem_raw + p.off_used;                       // [2*capP]
-    int *s_misc = reinterpret_cast<int *>(smem_raw + p.off_misc);        // [16]: warp counts, totals
-    Cand *cand0, *cand1;
+    const Span<int2> s_pa = SPAN(int2, reinterpret_cast<int2 *>(smem_raw + p.off_pk), capP);          // [capP]
+    const Span<int2> s_pb = SPAN(int2, reinterpret_cast<int2 *>(smem_raw + p.off_pk) + capP, capP);   // [capP]
+    const Span<unsigned char> s_used = SPAN(unsigned char, smem_raw + p.off_used, 2 * capP);         // [2*capP]
+    const Span<int> s_misc = SPAN(int, reinterpret_cast<int *>(smem_raw + p.off_misc), 16);          // [16]: warp counts, totals
+    Cand *cand0_, *cand1_;
     if (p.cand_in_smem) {
-        cand0 = reinterpret_cast<Cand *>(smem_raw + p.off_cand);
-        cand1 = reinterpret_cast<Cand *>(smem_raw + p.off_cand1); // the PAF tile's bytes: written only after the scoring loop
+        cand0_ = reinterpret_cast<Cand *>(smem_raw + p.off_cand);
+        cand1_ = reinterpret_cast<Cand *>(smem_raw + p.off_cand1); // the PAF tile's bytes: written only after the scoring loop
     } else {
-        cand0 = reinterpret_cast<Cand *>(p.cand_scratch) + ((size_t)frame * OPP_N_PAIRS + pair_id) * 2 * capC;
-        cand1 = cand0 + capC;
+        cand0_ = reinterpret_cast<Cand *>(p.cand_scratch) + ((size_t)frame * OPP_N_PAIRS + pair_id) * 2 * capC;
+        cand1_ = cand0_ + capC;
     }
+    const Span<Cand> cand0 = SPAN(Cand, cand0_, capC), cand1 = SPAN(Cand, cand1_, capC);
 
     stamp(p, frame, pair_id, 0);
     if (p.times && tid == 0) { // which SM ran this CTA (slot 11)
@@ -2237,13 +2271,13 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
         stamp(p, frame, pair_id, 1);
 
         PairCtx pc;
-        pc.px = px_plane, pc.py = py_plane, pc.g = &p.g, pc.w = w, pc.H = p.g.H, pc.thr = p.thr_vec;
+        pc.px = SPAN(const float, px_plane, h * w), pc.py = SPAN(const float, py_plane, h * w), pc.g = &p.g, pc.w = w, pc.H = p.g.H, pc.thr = p.thr_vec;
         pc.sshift = (p.g.S > 0 && (p.g.S & (p.g.S - 1)) == 0) ? 31 - __clz(p.g.S) : -1;
-        pc.steps = p.steps_in_smem ? reinterpret_cast<const float *>(smem_raw + p.off_steps) : nullptr;
-        pc.weak = nullptr;
+        pc.steps = SPAN(const float, p.steps_in_smem ? reinterpret_cast<const float *>(smem_raw + p.off_steps) : nullptr, max(p.g.H, p.g.W));
+        pc.weak = SPAN(const unsigned, nullptr, 0);
         if (p.weak_in_smem && pc.sshift >= 0 && p.g.W < (1 << 22) && p.g.H < (1 << 22)) {
             // cells whose PAF is too small for any sample to pass (see pair_may_pass)
-            unsigned *wk = reinterpret_cast<unsigned *>(smem_raw + p.off_weak);
+            const Span<unsigned> wk = SPAN(unsigned, reinterpret_cast<unsigned *>(smem_raw + p.off_weak), (h * w + 31) / 32);
             const float tw = __fmul_rn(p.thr_vec, 1.f - 1.f / 8192.f);
             for (int base = warp * 32; base < h * w; base += blockDim.x) {
                 const int cidx = base + lane;
@@ -2251,10 +2285,10 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
                 const unsigned m = __ballot_sync(0xffffffffu, wkb);
                 if (lane == 0) wk[base >> 5] = m;
             }
-            pc.weak = wk;
+            pc.weak = SPAN(const unsigned, wk.p, (h * w + 31) / 32);
             __syncthreads();
         }
-        int *s_surv = reinterpret_cast<int *>(smem_raw + p.off_surv); // [surv_cap] pairs that passed the quick test
+        const Span<int> s_surv = SPAN(int, reinterpret_cast<int *>(smem_raw + p.off_surv), p.surv_cap); // [surv_cap] pairs that passed the quick test
         const unsigned n_pairs_u = (unsigned)n_pairs, nb_u = (unsigned)nb;
         const unsigned lt = (1u << lane) - 1;
         // idx -> (ia, ib) without an integer division: q = floor(idx * floor(2^32 / nb) / 2^32) is ia or ia - 1
@@ -2273,7 +2307,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
             // Candidates are appended in whatever order the warps finish (one shared-memory atomic per warp and round,
             // no block-wide compaction); the sort below ranks them by (score, pair index), which is std::sort's
             // result whenever no two scores are equal, and restores the a-major / b-minor input order first when some are.
-            int *s_cnt = s_misc + 12; // [0] survivors in the list, [1] candidates appended
+            const Span<int> s_cnt = s_misc.from(12); // [0] survivors in the list, [1] candidates appended
             if (tid == 0) s_cnt[0] = 0, s_cnt[1] = 0;
             __syncthreads();
             auto drain = [&]() { // the listed survivors in full; whole CTA
@@ -2324,7 +2358,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
                         unsigned ia, ib;
                         split(idx, ia, ib);
                         float unused;
-                        alive = pc.weak ? pair_may_pass(pc, s_pa[ia], s_pb[ib]) : score_pair<true>(pc, s_pa[ia], s_pb[ib], unused);
+                        alive = pc.weak.p ? pair_may_pass(pc, s_pa[ia], s_pb[ib]) : score_pair<true>(pc, s_pa[ia], s_pb[ib], unused);
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, alive);
                     if (m) {
@@ -2409,7 +2443,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
 
         // ---- sort by score, descending, in std::sort's order.  With no equal scores the sorted order is
         // unique and a parallel rank sort gives it; with ties only the sequential emulation does.
-        Cand *sorted = cand0;
+        Span<Cand> sorted = cand0;
         if (n_cand > 1) {
             int tie = 0;
             if (n_cand <= 4096) {
@@ -2447,8 +2481,9 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
                 }
                 if (tie && p.cand_in_smem && n_cand <= 0xffff) {
                     // tied scores: std::sort's element movement decides.  cand1 serves as scratch in between.
-                    unsigned short *pos_a = reinterpret_cast<unsigned short *>(cand1), *pos_b = pos_a + n_cand;
-                    std_sort_partition_rounds(cand0, n_cand, pos_a, pos_b, reinterpret_cast<int *>(smem_raw + p.off_surv));
+                    const Span<unsigned short> pos_a = SPAN(unsigned short, reinterpret_cast<unsigned short *>(cand1.p), n_cand);
+                    const Span<unsigned short> pos_b = SPAN(unsigned short, reinterpret_cast<unsigned short *>(cand1.p) + n_cand, n_cand);
+                    std_sort_partition_rounds(cand0, n_cand, pos_a, pos_b, SPAN(int, reinterpret_cast<int *>(smem_raw + p.off_surv), p.surv_cap));
                     rank_sort();
                     tie = 0;
                 }
@@ -2456,7 +2491,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
                 tie = 1;
             if (tie) {
                 sorted = cand0;
-                if (tid == 0) std_sort_desc(cand0, n_cand);
+                if (tid == 0) std_sort_desc(cand0.p, n_cand);
                 __syncthreads();
             }
         }
@@ -2470,11 +2505,11 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
         // all candidates in a handful of rounds on real frames; the position in sorted order is the only priority, so
         // ties in the scores change nothing here.  Whatever is still undecided after GREEDY_ROUNDS is finished by the
         // sequential loop; the accepted candidates are then written in sorted (= acceptance) order.
-        opp_conn_t *conns = p.conns + ((size_t)frame * OPP_N_PAIRS + pair_id) * capP;
+        const Span<opp_conn_t> conns = SPAN(opp_conn_t, p.conns + ((size_t)frame * OPP_N_PAIRS + pair_id) * capP, capP);
         constexpr int GREEDY_ROUNDS = 6;
-        unsigned char *s_state = reinterpret_cast<unsigned char *>(smem_raw + p.off_surv); // [n_cand] 0 undecided, 1 accepted, 2 rejected
+        const Span<unsigned char> s_state = SPAN(unsigned char, reinterpret_cast<unsigned char *>(smem_raw + p.off_surv), p.surv_cap * 4); // [n_cand] 0 undecided, 1 accepted, 2 rejected
         if (n_cand > 32 && n_cand <= p.surv_cap * 4) {
-            int *s_first = s_ka; // [2 capP] first undecided candidate of every peak (the key lists are dead by now)
+            const Span<int> s_first = s_ka; // [2 capP] first undecided candidate of every peak (the key lists are dead by now)
             for (int t = tid; t < n_cand; t += blockDim.x) s_state[t] = 0;
             int left = 1;
             for (int round = 0; round < GREEDY_ROUNDS && left; ++round) {
@@ -2819,6 +2854,23 @@ cudaError_t launch_ingest(const float *src0, float *dst0, size_t n0, const float
     if (blocks < 1) blocks = 1;
     k0_ingest<<<(unsigned)blocks, OPP_THREADS, 0, st>>>(src0, dst0, n0, src1, dst1, n1, counters, n_counters);
     return cudaGetLastError();
+}
+
+// First bounds violation recorded by a -DOPP_DEBUG_BOUNDS build on the current device: {source line of the Span, index,
+// size, number of violations}; cudaErrorNotSupported in a release build.
+cudaError_t opp_kernels_bounds_report(int out[4], bool reset)
+{
+#ifdef OPP_DEBUG_BOUNDS
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyFromSymbol(out, g_oob, 4 * sizeof(int));
+    if (e != cudaSuccess || !reset) return e;
+    const int zero[4] = {0, 0, 0, 0};
+    return cudaMemcpyToSymbol(g_oob, zero, sizeof zero);
+#else
+    (void)out, (void)reset;
+    return cudaErrorNotSupported;
+#endif
 }
 
 cudaError_t opp_kernels_init(int max_smem_optin)

@@ -118,3 +118,4 @@ cudaError_t launch_hwc_to_chw(const float *src, float *dst, int n, int C, int h,
 cudaError_t launch_ingest(const float *src0, float *dst0, size_t n0, const float *src1, float *dst1, size_t n1, int *counters, int n_counters,
                           cudaStream_t st);
 cudaError_t opp_kernels_init(int max_smem_optin);
+cudaError_t opp_kernels_bounds_report(int out[4], bool reset);

@@ -178,6 +178,13 @@ class Engine:
     def last_batch_ms(self, ticket):
         return float(self.L.opp_last_batch_ms(self.h, ticket))
 
+    def bounds_report(self):
+        """(line, index, size, violations) of the first out-of-bounds access a bounds-checked build recorded since the
+        last call (all 0: none); OppError on a release build.  See opp_debug_bounds_report."""
+        out = (C.c_int32 * 4)()
+        self._check(self.L.opp_debug_bounds_report(self.h, out))
+        return tuple(out)
+
     def peak_kernel(self):
         """'fast' | 'generic_rep' | 'generic': the peak kernel opp_create selected (opp_peak_kernel)."""
         return self.L.opp_peak_kernel(self.h).decode()

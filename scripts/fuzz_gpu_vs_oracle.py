@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """GPU fuzz: the CUDA path against the CPU oracle on random geometries (integer and non-integer scales), kernel sizes,
 both variants, crowd sizes, missing limbs, noise and quantised (tie-rich) maps, one- to five-frame batches, pinned and
-pageable buffers.  Every stage is compared (tests/helpers.check_frame).   python scripts/fuzz_gpu_vs_oracle.py [seconds] [seed]"""
+pageable buffers, several capacity sets (the limb kernel takes different code paths with them), with and without the
+up-sampled maps materialised.  Every stage is compared (tests/helpers.check_frame).
+    python scripts/fuzz_gpu_vs_oracle.py [seconds] [seed]
+With OPP_B200_LIB=openpose_plus_b200/libopp_b200_dbg.so (python -m openpose_plus_b200.build --debug) every shared-memory
+array access of the kernels is bounds-checked as well and violations are reported (opp_debug_bounds_report)."""
 import os
 import sys
 import time
@@ -18,7 +22,8 @@ import helpers  # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
-t0, n_frames, n_cfg, n_over, bad = time.time(), 0, 0, 0, []
+t0, n_frames, n_cfg, n_over, bad, oob = time.time(), 0, 0, 0, [], []
+checked = None  # is this a bounds-checked build?
 while time.time() - t0 < budget:
     fh, fw = [(46, 54), (23, 27), (30, 40), (12, 14)][int(rng.integers(4))]
     kind = int(rng.integers(6))
@@ -26,7 +31,7 @@ while time.time() - t0 < budget:
     oh, ow = fh * scale, fw * scale
     if kind == 5:
         oh, ow = int(fh * rng.uniform(1.0, 6.0)), int(fw * rng.uniform(1.0, 6.0))
-    k = int(rng.choice([1, 3, 5, 7, 9, 13, 17, 25, 31]))
+    k = int(rng.choice([1, 3, 5, 7, 9, 13, 17, 19, 21, 25, 31, 33, 37]))
     if k <= 7 and (scale > 2 or kind in (3, 5)):
         continue
     if k // 2 >= min(oh, ow) - 1:
@@ -53,18 +58,37 @@ while time.time() - t0 < budget:
         hc[...], hp[...] = conf, paf
     else:
         hc, hp = conf, paf
-    eng = Engine(fh, fw, oh, ow, k, max_batch=5, max_peaks_per_part=512, max_cands_per_limb=8192, max_humans=512, variant=variant)
+    capP, capC, capH = [(512, 8192, 512), (512, 4096, 512), (128, 1024, 128), (256, 2048, 256)][int(rng.integers(4))]
+    eng = Engine(fh, fw, oh, ow, k, max_batch=5, max_peaks_per_part=capP, max_cands_per_limb=capC, max_humans=capH, variant=variant)
     orc = Oracle(fh, fw, oh, ow, k, variant=variant)
+    kw = {}
+    if rng.integers(4) == 0:
+        import torch
+        kw = dict(conf_up=torch.empty((nb, 19, oh, ow), device="cuda"), paf_up=torch.empty((nb, 38, oh, ow), device="cuda"))
+    what = "fuzz %s" % ((fh, fw, oh, ow, k, variant, kind, nb, capP, capC, capH, bool(kw)),)
     try:
-        helpers.run_and_check(eng, orc, hc, hp, "fuzz %s" % ((fh, fw, oh, ow, k, variant, kind, nb),))
+        helpers.run_and_check(eng, orc, hc, hp, what, **kw)
+        if kw:
+            o = orc.run(conf[nb - 1], paf[nb - 1], maps=True)
+            assert np.array_equal(kw["conf_up"][nb - 1].cpu().numpy(), o["conf_up"]) and np.array_equal(kw["paf_up"][nb - 1].cpu().numpy(), o["paf_up"]), what + ": up-sampled maps differ"
     except AssertionError as e:
         if "capacity overflow" in str(e):  # tie-rich maps can exceed the capacities chosen above: flagged, not a disagreement
             n_over += 1
         else:
             bad.append(str(e))
             print("MISMATCH", e, flush=True)
+    if checked is not False:
+        try:
+            rec = eng.bounds_report()
+            checked = True
+            if rec[3]:
+                oob.append((what, rec))
+                print("OUT OF BOUNDS", what, "line %d index %d size %d (%d violations)" % rec, flush=True)
+        except capi.OppError:
+            checked = False
     eng.close()
     n_frames += nb
     n_cfg += 1
-print("configurations %d, frames %d, batches over capacity (flagged) %d, mismatches %d" % (n_cfg, n_frames, n_over, len(bad)))
-sys.exit(1 if bad else 0)
+print("configurations %d, frames %d, batches over capacity (flagged) %d, mismatches %d, bounds-checked build: %s, out-of-bounds accesses in %d configurations"
+      % (n_cfg, n_frames, n_over, len(bad), bool(checked), len(oob)))
+sys.exit(1 if bad or oob else 0)
