@@ -571,17 +571,18 @@ def main():
     if rank == 0 and world == 1 and not args.no_other_configs:
         from openpose_plus_b200 import synth
 
-        def other_config(fh, fw, people, batch, materialize, steps=40, inputs=None, env=None, **kw):
+        def other_config(fh, fw, people, batch, materialize, steps=40, inputs=None, env=None, out_hw=None, **kw):
+            oh, ow = out_hw if out_hw else (8 * fh, 8 * fw)
             conf, paf = inputs if inputs is not None else synth.render_batch(batch, n_people=people, feat_h=fh, feat_w=fw, seed0=2000, pool=8)
             dc, dp = torch.from_numpy(conf).to(dev), torch.from_numpy(paf).to(dev)
             for k_, v_ in (env or {}).items():
                 os.environ[k_] = v_
             try:
-                e2 = Engine(fh, fw, max_batch=batch, device=local, n_slots=S, **kw)
+                e2 = Engine(fh, fw, oh, ow, max_batch=batch, device=local, n_slots=S, **kw)
             finally:
                 for k_ in (env or {}):
                     del os.environ[k_]
-            ups = [(torch.empty((batch, 19, 8 * fh, 8 * fw), device=dev), torch.empty((batch, 38, 8 * fh, 8 * fw), device=dev)) for _ in range(S)] if materialize else None
+            ups = [(torch.empty((batch, 19, oh, ow), device=dev), torch.empty((batch, 38, oh, ow), device=dev)) for _ in range(S)] if materialize else None
             o2 = [(capi.pinned_empty((batch, e2.max_humans), capi.HUMAN_DT), capi.pinned_empty((batch,), np.int32), capi.pinned_empty((batch,), np.int32)) for _ in range(S)]
 
             def go(n):
@@ -603,7 +604,7 @@ def main():
                 ms = t if ms is None else min(ms, t)
             assert not (o2[0][2] & capi.FLAG_OVERFLOW_MASK).any(), "capacity overflow in a bench configuration"
             kernel_ms = None
-            if materialize and batch == BATCH and fh == FEAT_H:   # the fused peak + resize kernel of this input alone
+            if materialize and batch == BATCH and fh == FEAT_H and not out_hw:   # the fused peak + resize kernel of this input alone
                 try:
                     kernel_ms = time_kernel(kernel_fns(e2, [(dc, dp)], ups)[2], 50)
                 except capi.OppError:   # configurations the integer-scale kernel does not cover have no stand-alone entry
@@ -616,8 +617,9 @@ def main():
         def pair(fh, fw, people, batch, **kw):
             m, kms = other_config(fh, fw, people, batch, True, **kw)
             s_, _ = other_config(fh, fw, people, batch, False, **kw)
+            oh, ow = kw.get("out_hw") or (8 * fh, 8 * fw)
             d = {"materialised": m, "skeleton_only": s_, "unit": "frames/s",
-                 "materialised_hbm_frac": m * 4 * 57 * (fh * fw + 64 * fh * fw) / 1e9 / peak}
+                 "materialised_hbm_frac": m * 4 * 57 * (fh * fw + oh * ow) / 1e9 / peak}
             if kms:
                 d["fused_kernel_ms"] = kms
                 d["fused_kernel_hbm_frac"] = gbs(kms) / peak
@@ -630,6 +632,8 @@ def main():
             # pafprocess-style grouping)
             "368x432_b64_python_variant_k25": pair(46, 54, PEOPLE, 64, gauss_kernel_size=25, variant=capi.VARIANT_PYTHON),
             "368x432_b64_cpp_k25": pair(46, 54, PEOPLE, 64, gauss_kernel_size=25),
+            # a non-integer scale (46x54 -> 300x400): cv::resize's 2-tap area-mode form, the generic peak kernel
+            "300x400_b64_non_integer_scale": pair(46, 54, PEOPLE, 64, out_hw=(300, 400)),
         }
         # configs[1] when the block skipping of the peak kernel finds nothing to skip: (a) a uniform noise floor in
         # [0.03, 0.07] under the rendered maps (what a CNN's heat maps look like away from the joints), (b) skipping off

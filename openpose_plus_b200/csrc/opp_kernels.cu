@@ -2754,7 +2754,14 @@ cudaError_t launch_k3(const K3Params &p, int n_frames, size_t smem, cudaStream_t
     BIG_SMEM_LIMIT(k3_limbs, dyn_limit);
     if (smem > (size_t)dyn_limit) return cudaErrorInvalidValue;
     dim3 grid(OPP_N_PAIRS, n_frames);
-    return launch_ex(k3_limbs, grid, dim3(OPP_THREADS), smem, st, pdl, p);
+    // OPP_K3_THREADS (128 .. 256, multiple of 32): threads per limb CTA.  Smaller CTAs fit beside the peak kernel's CTAs
+    // on an SM (registers are what keeps a 256-thread CTA out while three store-mode peak CTAs are resident).
+    static const int threads = [] {
+        const char *e = getenv("OPP_K3_THREADS");
+        const int t = e ? atoi(e) : OPP_THREADS;
+        return (t >= 128 && t <= OPP_THREADS && t % 32 == 0) ? t : OPP_THREADS;
+    }();
+    return launch_ex(k3_limbs, grid, dim3(threads), smem, st, pdl, p);
 }
 
 static bool k1_fast_ok(const K1Params &p)

@@ -81,6 +81,21 @@ def test_non_integer_scales_from_feature_maps_and_from_the_materialised_map(mods
             eng.close()
 
 
+def test_dense_noise_frame(mods):
+    """SURVEY 8(d)'s capacity-sizing frame: uniform-random maps (7 847 peaks, ~195 k candidate pairs and ~1 700 accepted
+    candidates per limb, four limbs with tied scores, 1 300 partial humans, 99 merges).  Far beyond the staging areas of the
+    assembly (connections and peaks are then read limb by limb / from global memory) and, with the second capacity set,
+    beyond the shared-memory candidate buffers (ordered compaction, sequential std::sort emulation): every stage bit-exact."""
+    Engine, Oracle, H = mods
+    conf, paf = synth.noise_frame(3)
+    orc = Oracle(46, 54, 368, 432, 17)
+    for (capP, capC, capH) in ((512, 2048, 1536), (512, 8192, 1536)):
+        eng = Engine(46, 54, max_batch=1, max_peaks_per_part=capP, max_cands_per_limb=capC, max_humans=capH)
+        humans, counts, flags = H.run_and_check(eng, orc, conf[None], paf[None], "dense noise caps %d/%d/%d" % (capP, capC, capH))
+        assert counts[0] > 500
+        eng.close()
+
+
 def test_values_around_the_peak_threshold(mods):
     """The peak kernel skips blocks that provably stay below THRESH_HEAT; maps whose smoothed maxima sit
     just below / just above 0.05, flat backgrounds near it, and isolated spikes must still be bit-exact."""
