@@ -171,6 +171,11 @@ def make_ring(pool, n_batches):
     return ring
 
 
+def make_inputs(n_batches):
+    """`n_batches` distinct 64-frame batches of configs[1] (what the probe scripts under scripts/ feed the engine)."""
+    return make_ring(render_pool(), n_batches)
+
+
 def run_reference(args, rank):
     """The reference's own CPU implementation on all host cores (rank 0 only)."""
     if rank != 0:

@@ -515,17 +515,10 @@ struct Win9 {
 
 // Operands for cell i of n along one axis: (m2, m1, z, p1, p2) = cells i-2 .. i+2 (anything where the cell does
 // not exist: such a value is never selected).  NB = neighbour depth (1: R <= S, 2: S < R <= 2S; needs n >= NB + 1).
-// INTERIOR: the caller knows NB <= i < n - NB, so every operand is the plain neighbour (no selects, and the *s operands
-// are the same values as their neighbours: their tap products merge).
-template <int NB, bool BZ, bool INTERIOR = false>
+template <int NB, bool BZ>
 __device__ __forceinline__ Win9 make_win(float m2, float m1, float z, float p1, float p2, int i, int n)
 {
     Win9 v;
-    if (INTERIOR) {
-        v.b = z, v.a = v.as = m1, v.c = v.cs = p1;
-        v.a2 = v.a2s = NB > 1 ? m2 : 0.f, v.c2 = v.c2s = NB > 1 ? p2 : 0.f;
-        return v;
-    }
     const bool lo1 = i > 0, hi1 = i < n - 1;
     v.b = z;
     if (BZ) {
@@ -836,15 +829,9 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
             float out[S];
             const float m2 = NB > 1 ? Lr[max(c - 2, 0)] : 0.f, m1 = Lr[max(c - 1, 0)], p1 = Lr[min(c + 1, w - 1)], p2 = NB > 1 ? Lr[min(c + 2, w - 1)] : 0.f;
             constexpr bool kRowPacked = R > 2 || BZ; // the symmetric-small forms (k = 3, 5) stay as OpenCV writes them
-            if (c >= NB && c + NB < w) { // interior cell: plain neighbours
-                const Win9 win = make_win<NB, BZ, true>(m2, m1, Lr[c], p1, p2, c, w);
-                if (kRowPacked) row_taps2<S, R>(p.taps, win, out);
-                else row_taps<S, R, BZ>(p.taps, win, out);
-            } else {
-                const Win9 win = make_win<NB, BZ>(m2, m1, Lr[c], p1, p2, c, w);
-                if (kRowPacked) row_taps2<S, R>(p.taps, win, out);
-                else row_taps<S, R, BZ>(p.taps, win, out);
-            }
+            const Win9 win = make_win<NB, BZ>(m2, m1, Lr[c], p1, p2, c, w);
+            if (kRowPacked) row_taps2<S, R>(p.taps, win, out);
+            else row_taps<S, R, BZ>(p.taps, win, out);
             float *d = &Rrow[r * RW + S * (c - jlo)];
             if (S % 4 == 0) {
 #pragma unroll
@@ -921,15 +908,10 @@ __global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peak
         };
         auto smooth_rows = [&](int i, float (&s0)[S], float (&s1)[S]) { // the S image rows of feature row i, both columns
             w0[NW - 1] = ldr0(i + NB), w1[NW - 1] = ldr1(i + NB);
-            if (i >= NB && i + NB < h) { // interior feature row (all but NB at either end): plain neighbours, no selects
-                const Win9 v0 = make_win<NB, BZ, true>(w0[0], w0[NB - 1], w0[NB], w0[NB + 1], w0[NW - 1], i, h);
-                const Win9 v1 = make_win<NB, BZ, true>(w1[0], w1[NB - 1], w1[NB], w1[NB + 1], w1[NW - 1], i, h);
-                col_all2<S, R>(p.taps, v0, v1, s0, s1);
-            } else {
-                const Win9 v0 = make_win<NB, BZ>(w0[0], w0[NB - 1], w0[NB], w0[NB + 1], w0[NW - 1], i, h);
-                const Win9 v1 = make_win<NB, BZ>(w1[0], w1[NB - 1], w1[NB], w1[NB + 1], w1[NW - 1], i, h);
-                col_all2<S, R>(p.taps, v0, v1, s0, s1);
-            }
+            // (a select-free copy of this for interior rows was tried: no faster, and twice the code to fetch)
+            const Win9 v0 = make_win<NB, BZ>(w0[0], w0[NB - 1], w0[NB], w0[NB + 1], w0[NW - 1], i, h);
+            const Win9 v1 = make_win<NB, BZ>(w1[0], w1[NB - 1], w1[NB], w1[NB + 1], w1[NW - 1], i, h);
+            col_all2<S, R>(p.taps, v0, v1, s0, s1);
         };
         const int i_first = ia > 0 ? ia - 1 : ia;
         load_window(i_first);
@@ -1437,7 +1419,10 @@ __device__ __forceinline__ bool score_pair(const PairCtx &c, const int2 A, const
     const float step_y = c.steps.p ? copysignf(c.steps[abs(dy)], (float)dy) : __fdiv_rn((float)dy, 10.f);
     float scores = 0.f;
     int cnt = 0;
-#pragma unroll
+    // Not unrolled all the way: the limb kernel runs most of its code once or a few times per CTA, i.e. cold, and
+    // straight-line code costs more in instruction fetch than the loop costs in issue slots (10 samples unrolled: +1.5 us
+    // per limb CTA on the one-frame latency path, -7 % throughput on crowded batches).
+#pragma unroll 2
     for (int i = QUICK ? 3 : 0; i < (QUICK ? 7 : 10); ++i) {
         // roundpaf(peak1.x + i * STEP_X): float mul, float add, double +0.5, truncate  :325-326,337
         const float fx = __fadd_rn((float)A.x, __fmul_rn((float)i, step_x));
@@ -1549,7 +1534,7 @@ __device__ void insertion_sort_range(Cand *first, Cand *last)
     }
 }
 
-__device__ void std_sort_desc(Cand *v, int n)
+__device__ __noinline__ void std_sort_desc(Cand *v, int n)
 {
     if (n <= 0) return;
     struct Range {
@@ -1617,7 +1602,7 @@ __device__ void std_sort_desc(Cand *v, int n)
 //   * a range whose depth budget is spent is heap-sorted sequentially, as libstdc++ does.
 // What remains (__final_insertion_sort) is an insertion sort = the stable order of the array left behind, which the
 // caller produces with a rank sort.  pos_a / pos_b: scratch, n entries each; rng: scratch, 4 (n / 17 + 2) ints.
-__device__ void std_sort_partition_rounds(const Span<Cand> v, int n, const Span<unsigned short> pos_a, const Span<unsigned short> pos_b, const Span<int> rng)
+__device__ __noinline__ void std_sort_partition_rounds(const Span<Cand> v, int n, const Span<unsigned short> pos_a, const Span<unsigned short> pos_b, const Span<int> rng)
 {
     __shared__ int s_rcnt[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -2260,7 +2245,10 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
             px_plane = s_paf, py_plane = s_paf + h * w;
         }
         for (int t = tid; t < 2 * capP; t += blockDim.x) s_used[t] = 0;
-        if (p.steps_in_smem) { // d / 10.f for every coordinate difference the image allows
+        // the step table and the weak-cell map pay for themselves from a few hundred pairs on (a frame with five people has
+        // ~25 pairs per limb: there they would only add to the one-frame latency)
+        const bool many_pairs = n_pairs >= 512;
+        if (p.steps_in_smem && many_pairs) { // d / 10.f for every coordinate difference the image allows
             float *st = reinterpret_cast<float *>(smem_raw + p.off_steps);
             for (int t = tid; t < max(p.g.H, p.g.W); t += blockDim.x) st[t] = __fdiv_rn((float)t, 10.f);
         }
@@ -2273,9 +2261,9 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
         PairCtx pc;
         pc.px = SPAN(const float, px_plane, h * w), pc.py = SPAN(const float, py_plane, h * w), pc.g = &p.g, pc.w = w, pc.H = p.g.H, pc.thr = p.thr_vec;
         pc.sshift = (p.g.S > 0 && (p.g.S & (p.g.S - 1)) == 0) ? 31 - __clz(p.g.S) : -1;
-        pc.steps = SPAN(const float, p.steps_in_smem ? reinterpret_cast<const float *>(smem_raw + p.off_steps) : nullptr, max(p.g.H, p.g.W));
+        pc.steps = SPAN(const float, p.steps_in_smem && many_pairs ? reinterpret_cast<const float *>(smem_raw + p.off_steps) : nullptr, max(p.g.H, p.g.W));
         pc.weak = SPAN(const unsigned, nullptr, 0);
-        if (p.weak_in_smem && pc.sshift >= 0 && p.g.W < (1 << 22) && p.g.H < (1 << 22)) {
+        if (p.weak_in_smem && many_pairs && pc.sshift >= 0 && p.g.W < (1 << 22) && p.g.H < (1 << 22)) {
             // cells whose PAF is too small for any sample to pass (see pair_may_pass)
             const Span<unsigned> wk = SPAN(unsigned, reinterpret_cast<unsigned *>(smem_raw + p.off_weak), (h * w + 31) / 32);
             const float tw = __fmul_rn(p.thr_vec, 1.f - 1.f / 8192.f);
@@ -2310,9 +2298,10 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
             const Span<int> s_cnt = s_misc.from(12); // [0] survivors in the list, [1] candidates appended
             if (tid == 0) s_cnt[0] = 0, s_cnt[1] = 0;
             __syncthreads();
-            auto drain = [&]() { // the listed survivors in full; whole CTA
+            // direct = true: no list, the first n_direct pairs themselves (limbs with few pairs skip the filter stage)
+            auto drain = [&](bool direct, int n_direct) { // the listed survivors in full; whole CTA
                 __syncthreads();
-                const int n_surv = min(s_cnt[0], p.surv_cap);
+                const int n_surv = direct ? n_direct : min(s_cnt[0], p.surv_cap);
                 n_surv_total += n_surv;
                 for (int base = warp * 32; base < n_surv; base += blockDim.x) {
                     const int t = base + lane;
@@ -2320,7 +2309,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
                     float crit2 = 0.f;
                     unsigned ia = 0, ib = 0;
                     if (t < n_surv) {
-                        split((unsigned)s_surv[t], ia, ib);
+                        split(direct ? (unsigned)t : (unsigned)s_surv[t], ia, ib);
                         accept = score_pair<false>(pc, s_pa[ia], s_pb[ib], crit2);
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, accept);
@@ -2345,10 +2334,10 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
             };
             const unsigned chunk = (unsigned)(p.surv_cap / 2) & ~255u; // pairs per round of quick tests: the list never overflows
             unsigned listed_max = 0;                                    // upper bound of the survivors listed so far
-            for (unsigned c0 = 0; c0 < n_pairs_u; c0 += chunk) {
+            for (unsigned c0 = 0; many_pairs && c0 < n_pairs_u; c0 += chunk) {
                 const unsigned c1 = min(c0 + chunk, n_pairs_u);
                 if (listed_max + (c1 - c0) > (unsigned)p.surv_cap) {
-                    drain();
+                    drain(false, 0);
                     listed_max = 0;
                 }
                 for (unsigned base = c0 + warp * 32; base < c1; base += blockDim.x) {
@@ -2370,7 +2359,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
                 }
                 listed_max += c1 - c0;
             }
-            drain();
+            drain(!many_pairs, (int)n_pairs_u);
             n_cand = s_cnt[1];
         } else {
         // ordered block compaction: the threads with `flag` learn their position after the `count` entries already
@@ -2754,12 +2743,14 @@ cudaError_t launch_k3(const K3Params &p, int n_frames, size_t smem, cudaStream_t
     BIG_SMEM_LIMIT(k3_limbs, dyn_limit);
     if (smem > (size_t)dyn_limit) return cudaErrorInvalidValue;
     dim3 grid(OPP_N_PAIRS, n_frames);
-    // OPP_K3_THREADS (128 .. 256, multiple of 32): threads per limb CTA.  Smaller CTAs fit beside the peak kernel's CTAs
-    // on an SM (registers are what keeps a 256-thread CTA out while three store-mode peak CTAs are resident).
+    // Threads per limb CTA (OPP_K3_THREADS = 128 .. 256, multiple of 32, overrides).  Most of the kernel is latency bound and
+    // leaves lanes idle (a frame with five people has 25 pairs per limb); 192-thread CTAs measured 4-5 % faster than 256 on
+    // typical and crowded batches alike (more CTAs fit beside the peak kernel's, whose registers are what keeps them out).
+    constexpr int K3_THREADS_DEFAULT = 192;
     static const int threads = [] {
         const char *e = getenv("OPP_K3_THREADS");
-        const int t = e ? atoi(e) : OPP_THREADS;
-        return (t >= 128 && t <= OPP_THREADS && t % 32 == 0) ? t : OPP_THREADS;
+        const int t = e ? atoi(e) : K3_THREADS_DEFAULT;
+        return (t >= 128 && t <= OPP_THREADS && t % 32 == 0) ? t : K3_THREADS_DEFAULT;
     }();
     return launch_ex(k3_limbs, grid, dim3(threads), smem, st, pdl, p);
 }

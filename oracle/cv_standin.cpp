@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE (oracle).  Definitions of the two OpenCV functions the reference's
 // src/post-process.h calls (cv::resize at :46-47, cv::GaussianBlur at :69-70), linked into
 // oracle/_ref/libopp_ref.so next to the reference's unmodified src/paf.cpp.  Both forward to the
-// scalar restatements in opp_oracle.c, which tests/test_oracle_cv.py holds bit-identical to
+// scalar restatements in opp_oracle.c, which tests/test_oracle_golden.py (test_against_live_cv2 and the committed tests/golden/opencv_pieces.npz) holds bit-identical to
 // cv2 4.13 (IPP off, setUseOptimized(False)).
 #include <cstdio>
 #include <cstdlib>
