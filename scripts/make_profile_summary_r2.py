@@ -107,3 +107,29 @@ if os.path.exists(pl):
     out.append("")
 open(os.path.join(P, "README_r2.md"), "w").write("\n".join(out))
 print("\n".join(out)[:3000])
+
+
+def opcode_mix(path, top=8):
+    """Share of the warp-stall SAMPLES per opcode (where the warps of the kernel spend their time) from a prof_*_sass.csv."""
+    import re
+    agg = collections.Counter()
+    for row in csv.reader(open(path)):
+        if len(row) < 4 or not row[0].startswith("0x"):
+            continue
+        nums = [c for c in row[2:] if re.fullmatch(r"\d+", c.strip())]
+        m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_]+)", row[1])
+        if nums and m:
+            agg[m.group(2)] += int(nums[0])
+    tot = sum(agg.values()) or 1
+    return ", ".join("%s %.0f %%" % (k, 100.0 * v / tot) for k, v in agg.most_common(top))
+
+
+mix = ["## Where the warps spend their time (stall samples per opcode; per-instruction tables kept as `r2_<name>_sass.csv` for four of them)\n", "| capture | opcodes by share of samples |\n|---|---|"]
+for k, name in have:
+    src = os.path.join(G, "prof_%s_sass.csv" % k)
+    if os.path.exists(src):
+        if k in ("k2store", "k2_dense", "k2_crowded", "k3_crowded"):  # the per-instruction tables of the kernels the text discusses (the rest: opcode shares only)
+            shutil.copy(src, os.path.join(P, "%s_%s_sass.csv" % (tag, k)))
+        mix.append("| `r2_%s` | %s |" % (k, opcode_mix(src)))
+with open(os.path.join(P, "README_r2.md"), "a") as f:
+    f.write("\n".join(mix) + "\n")
