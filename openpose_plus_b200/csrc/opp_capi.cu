@@ -212,7 +212,11 @@ void plan_k3_smem(opp_handle_s *h)
     const size_t fixed = 2 * (size_t)capP * sizeof(int2) + align_up(2 * (size_t)capP, 16) + 64;
     const size_t cand_bytes = 2 * (size_t)capC * 12;
     p.cand_in_smem = (fixed + cand_bytes) <= budget / 2;
-    p.paf_in_smem = (fixed + (p.cand_in_smem ? cand_bytes : 0) + paf_bytes) <= (size_t)(budget * 0.45);
+    // the second candidate buffer and the PAF tile share their bytes (below): the tile costs only what it exceeds that buffer by
+    {
+        const size_t c1 = p.cand_in_smem ? cand_bytes / 2 : 0, extra = paf_bytes > c1 ? paf_bytes - c1 : 0;
+        p.paf_in_smem = (fixed + (p.cand_in_smem ? cand_bytes : 0) + extra + 12 * 1024) <= budget / 2; // + survivors, steps, weak map
+    }
     // The PAF tile is dead once the limb's pairs are scored and the second candidate buffer (the sort's output) is
     // not written before that: the two share their bytes.
     p.off_paf = (int)off;
@@ -237,7 +241,7 @@ void plan_k3_smem(opp_handle_s *h)
     p.steps_in_smem = n_steps <= 1024;
     p.off_steps = (int)off;
     if (p.steps_in_smem) off += align_up(n_steps * sizeof(float), 16);
-    p.weak_in_smem = p.paf_in_smem && p.cand_unordered;
+    p.weak_in_smem = p.cand_unordered && ((size_t)g.h * g.w + 31) / 32 * sizeof(unsigned) <= 16 * 1024; // built from wherever the PAF planes are
     p.off_weak = (int)off;
     if (p.weak_in_smem) off += align_up((((size_t)g.h * g.w + 31) / 32) * sizeof(unsigned), 16);
     const size_t phase1 = off;

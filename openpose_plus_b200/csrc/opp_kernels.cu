@@ -678,7 +678,7 @@ __device__ __forceinline__ void stamp2(const K2Params &p, int slot)
 }
 
 template <int S, int R, bool STORE, bool BZ>
-__global__ void __launch_bounds__(K2_FAST_MAX_THREADS, K2_FAST_MIN_CTAS) k2_peaks_fast(const K2Params p)
+__global__ void __launch_bounds__(K2_FAST_MAX_THREADS, STORE ? K2_FAST_MIN_CTAS : K2_FAST_MIN_CTAS + 1) k2_peaks_fast(const K2Params p)
 {
     extern __shared__ __align__(16) float smem[];
     constexpr int NB = R > S ? 2 : 1; // neighbour depth: cells a tap can reach on either side
