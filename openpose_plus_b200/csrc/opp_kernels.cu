@@ -359,35 +359,36 @@ __global__ void __launch_bounds__(OPP_THREADS) k1_general_chw(const K1Params p)
     const float *plane = src + ((size_t)f * C + c) * h * w;
     float *out = dst + ((size_t)f * C + c) * (size_t)H * W;
     const int f_lo = clip_idx(g.yofs[y_a], h), f_hi = clip_idx(g.yofs[y_b - 1] + 1, h), nfr = f_hi - f_lo + 1;
-    for (int t = threadIdx.x; t < nfr * W; t += blockDim.x) {
-        const int fr = t / W, x = t - fr * W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // row buffers: a warp per feature row, lanes across it (no per-element division)
+    for (int fr = warp; fr < nfr; fr += nwarps) {
         const float *S0 = plane + (f_lo + fr) * w;
-        const int sx = g.xofs[x];
-        smem[t] = x < g.xmax ? __fadd_rn(__fmul_rn(S0[sx], g.alpha[2 * x]), __fmul_rn(S0[sx + 1], g.alpha[2 * x + 1])) : __fmul_rn(S0[sx], 1.f);
+        float *Trow = smem + fr * W;
+        for (int x = lane; x < W; x += 32) {
+            const int sx = g.xofs[x];
+            Trow[x] = x < g.xmax ? __fadd_rn(__fmul_rn(S0[sx], g.alpha[2 * x]), __fmul_rn(S0[sx + 1], g.alpha[2 * x + 1])) : __fmul_rn(S0[sx], 1.f);
+        }
     }
     __syncthreads();
+    // vertical blend: a warp per output row (source rows and coefficients once per row), 16-byte streaming stores
     const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    if (vec) {
-        const int W4 = W >> 2;
-        for (int t = threadIdx.x; t < (y_b - y_a) * W4; t += blockDim.x) {
-            const int r = t / W4, x4 = t - r * W4, y = y_a + r;
-            const int sy = g.yofs[y];
-            const float b0 = g.beta[2 * y], b1 = g.beta[2 * y + 1];
-            const float4 r0 = reinterpret_cast<const float4 *>(smem + (clip_idx(sy, h) - f_lo) * W)[x4];
-            const float4 r1 = reinterpret_cast<const float4 *>(smem + (clip_idx(sy + 1, h) - f_lo) * W)[x4];
-            float4 v;
-            v.x = __fadd_rn(__fmul_rn(r0.x, b0), __fmul_rn(r1.x, b1));
-            v.y = __fadd_rn(__fmul_rn(r0.y, b0), __fmul_rn(r1.y, b1));
-            v.z = __fadd_rn(__fmul_rn(r0.z, b0), __fmul_rn(r1.z, b1));
-            v.w = __fadd_rn(__fmul_rn(r0.w, b0), __fmul_rn(r1.w, b1));
-            __stcs(reinterpret_cast<float4 *>(out + (size_t)y * W) + x4, v);
-        }
-    } else {
-        for (int t = threadIdx.x; t < (y_b - y_a) * W; t += blockDim.x) {
-            const int r = t / W, x = t - r * W, y = y_a + r;
-            const int sy = g.yofs[y];
-            const float r0 = smem[(clip_idx(sy, h) - f_lo) * W + x], r1 = smem[(clip_idx(sy + 1, h) - f_lo) * W + x];
-            __stcs(out + (size_t)y * W + x, __fadd_rn(__fmul_rn(r0, g.beta[2 * y]), __fmul_rn(r1, g.beta[2 * y + 1])));
+    for (int y = y_a + warp; y < y_b; y += nwarps) {
+        const int sy = g.yofs[y];
+        const float b0 = g.beta[2 * y], b1 = g.beta[2 * y + 1];
+        const float *R0 = smem + (clip_idx(sy, h) - f_lo) * W, *R1 = smem + (clip_idx(sy + 1, h) - f_lo) * W;
+        float *orow = out + (size_t)y * W;
+        if (vec) {
+            for (int x4 = lane; x4 < (W >> 2); x4 += 32) {
+                const float4 r0 = reinterpret_cast<const float4 *>(R0)[x4], r1 = reinterpret_cast<const float4 *>(R1)[x4];
+                float4 v;
+                v.x = __fadd_rn(__fmul_rn(r0.x, b0), __fmul_rn(r1.x, b1));
+                v.y = __fadd_rn(__fmul_rn(r0.y, b0), __fmul_rn(r1.y, b1));
+                v.z = __fadd_rn(__fmul_rn(r0.z, b0), __fmul_rn(r1.z, b1));
+                v.w = __fadd_rn(__fmul_rn(r0.w, b0), __fmul_rn(r1.w, b1));
+                __stcs(reinterpret_cast<float4 *>(orow) + x4, v);
+            }
+        } else {
+            for (int x = lane; x < W; x += 32) __stcs(orow + x, __fadd_rn(__fmul_rn(R0[x], b0), __fmul_rn(R1[x], b1)));
         }
     }
 }
