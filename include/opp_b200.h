@@ -173,6 +173,11 @@ int64_t opp_launch_count(opp_handle_t h);
  * csrc/opp_kernels.cu, index, size, number of violations} (all 0: none) and clears the record.  OPP_ERR_INVALID in a
  * release build. */
 int opp_debug_bounds_report(opp_handle_t h, int32_t out[4]);
+/* Test entry for the limb kernel's emulation of std::sort(greater on score) (src/paf.cpp:151-152; libstdc++'s introsort: with
+ * tied scores its element movement decides the order): sorts cands[0..n) (host memory; cid1 / cid2 are carried along) in place
+ * on the device.  mode 0 = the parallel form the kernel uses for up to 4096 candidates in shared memory, 1 = the sequential
+ * emulation; threads = CTA size (multiple of 32, <= 256). */
+int opp_debug_sort(opp_handle_t h, opp_conn_t *cands, int n, int mode, int threads);
 /* Which peak kernel opp_create selected for this geometry and kernel size (a static string):
  *   "fast"        integer scale 8 or 4, Gaussian radius <= 2 x scale (k <= 33 at x8): reads the feature maps only
  *   "generic_rep" any other integer scale / larger kernels: replication-aware, reads the feature maps only

@@ -103,7 +103,7 @@ def lib():
 
 
 EXPORTS = ["opp_config_default", "opp_create", "opp_destroy", "opp_process", "opp_submit", "opp_wait",
-           "opp_last_batch_ms", "opp_launch_count", "opp_peak_kernel", "opp_debug_bounds_report", "opp_device", "opp_host_alloc", "opp_host_free", "opp_host_alloc_ex",
+           "opp_last_batch_ms", "opp_launch_count", "opp_peak_kernel", "opp_debug_bounds_report", "opp_debug_sort", "opp_device", "opp_host_alloc", "opp_host_free", "opp_host_alloc_ex",
            "opp_host_register", "opp_host_unregister", "opp_stream_wait_ticket", "opp_debug_fetch",
            "opp_resize_device", "opp_resize_pair_device", "opp_peaks_device", "opp_timer_start", "opp_timer_stop", "opp_last_error", "opp_version", "opp_draw_human", "opp_bench_latency", "opp_bench_h2d", "process_conf_paf"]
 

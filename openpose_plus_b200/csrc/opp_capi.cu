@@ -1135,6 +1135,24 @@ int opp_debug_bounds_report(opp_handle_t h, int32_t out[4])
     return OPP_OK;
 }
 
+int opp_debug_sort(opp_handle_t h, opp_conn_t *cands, int n, int mode, int threads)
+{
+    if (!h || !cands || n < 0) return OPP_ERR_INVALID;
+    DeviceGuard guard_(h->device);
+    void *d = nullptr;
+    CU(cudaMalloc(&d, (size_t)(n > 0 ? n : 1) * sizeof(opp_conn_t)));
+    cudaError_t e = cudaMemcpy(d, cands, (size_t)n * sizeof(opp_conn_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_debug_sort(d, n, mode, threads, nullptr);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(cands, d, (size_t)n * sizeof(opp_conn_t), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        set_err(&h->err, "opp_debug_sort: %s", cudaGetErrorString(e));
+        return e == cudaErrorInvalidValue ? OPP_ERR_INVALID : OPP_ERR_CUDA;
+    }
+    return OPP_OK;
+}
+
 const char *opp_peak_kernel(opp_handle_t h)
 {
     if (!h) return "";

@@ -1687,6 +1687,82 @@ __device__ __noinline__ void std_sort_partition_rounds(const Span<Cand> v, int n
     }
 }
 
+// The candidates of one limb in std::sort's order (src/paf.cpp:151-152), whole CTA.  cand0: the n candidates (in a-major /
+// b-minor order, or - `unordered` - in any order, identified by their pair index (i1 - ofs_a) * nb + (i2 - ofs_b));
+// cand1: a second buffer of the same size; scratch: 4 (n / 17 + 2) ints.  Returns whichever buffer holds the result.
+__device__ __forceinline__ Span<Cand> sort_candidates_desc(const Span<Cand> cand0, const Span<Cand> cand1, int n_cand, bool unordered, int ofs_a, int ofs_b,
+                                                           unsigned nb_u, bool in_smem, const Span<int> scratch)
+{
+    const int tid = threadIdx.x;
+    if (n_cand <= 1) return cand0;
+    int tie = 0;
+    if (n_cand <= 4096) {
+        // rank by (score descending, position ascending): the order itself when no two scores are equal, and
+        // the stable order = what __final_insertion_sort leaves when run after the partition rounds below
+        auto rank_sort = [&]() {
+            int any_tie = 0;
+            for (int t = tid; t < n_cand; t += blockDim.x) {
+                const float s = cand0[t].s;
+                int rank = 0;
+                for (int u = 0; u < n_cand; ++u) {
+                    const float su = cand0[u].s;
+                    rank += (su > s) | (su == s && u < t);
+                    any_tie |= (su == s && u != t);
+                }
+                cand1[rank] = cand0[t];
+            }
+            return __syncthreads_or(any_tie);
+        };
+        tie = rank_sort();
+        if (!tie) return cand1;
+        if (unordered) {
+            // std::sort's input is the candidate list in a-major / b-minor order (src/paf.cpp:93-131): put the
+            // unordered list into that order first (rank by pair index, which is unique), back into cand0
+            for (int t = tid; t < n_cand; t += blockDim.x) {
+                const Cand ct = cand0[t];
+                const unsigned key = (unsigned)(ct.i1 - ofs_a) * nb_u + (unsigned)(ct.i2 - ofs_b);
+                int rank = 0;
+                for (int u = 0; u < n_cand; ++u) rank += ((unsigned)(cand0[u].i1 - ofs_a) * nb_u + (unsigned)(cand0[u].i2 - ofs_b)) < key;
+                cand1[rank] = ct;
+            }
+            __syncthreads();
+            for (int t = tid; t < n_cand; t += blockDim.x) cand0[t] = cand1[t];
+            __syncthreads();
+        }
+        if (in_smem && n_cand <= 0xffff) {
+            // tied scores: std::sort's element movement decides.  cand1 serves as scratch in between.
+            const Span<unsigned short> pos_a = SPAN(unsigned short, reinterpret_cast<unsigned short *>(cand1.p), n_cand);
+            const Span<unsigned short> pos_b = SPAN(unsigned short, reinterpret_cast<unsigned short *>(cand1.p) + n_cand, n_cand);
+            std_sort_partition_rounds(cand0, n_cand, pos_a, pos_b, scratch);
+            rank_sort();
+            return cand1;
+        }
+    }
+    if (tid == 0) std_sort_desc(cand0.p, n_cand); // large lists, or lists in global memory: the sequential emulation
+    __syncthreads();
+    return cand0;
+}
+
+// Test entry: sorts n candidates (global memory, given order) the way the limb kernel does and writes them back in sorted
+// order.  mode 0: parallel form (shared memory, n <= 4096), 1: sequential emulation.  One CTA.
+__global__ void __launch_bounds__(OPP_THREADS) k_debug_sort(Cand *v, int n, int mode)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Span<Cand> c0 = SPAN(Cand, reinterpret_cast<Cand *>(smem_raw), n), c1 = SPAN(Cand, reinterpret_cast<Cand *>(smem_raw) + n, n);
+    const Span<int> scratch = SPAN(int, reinterpret_cast<int *>(c1.p + n), 4 * (n / 17 + 2));
+    Span<Cand> sorted = SPAN(Cand, v, n);
+    if (mode == 0) {
+        for (int t = threadIdx.x; t < n; t += blockDim.x) c0[t] = v[t];
+        __syncthreads();
+        sorted = sort_candidates_desc(c0, c1, n, false, 0, 0, 1u, true, scratch);
+    } else {
+        if (threadIdx.x == 0) std_sort_desc(v, n);
+    }
+    __syncthreads();
+    if (mode == 0)
+        for (int t = threadIdx.x; t < n; t += blockDim.x) v[t] = sorted[t];
+}
+
 __device__ __forceinline__ void stamp(const K3Params &p, int frame, int pair_id, int slot)
 {
     if (p.times && threadIdx.x == 0) {
@@ -2433,58 +2509,8 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
 
         // ---- sort by score, descending, in std::sort's order.  With no equal scores the sorted order is
         // unique and a parallel rank sort gives it; with ties only the sequential emulation does.
-        Span<Cand> sorted = cand0;
-        if (n_cand > 1) {
-            int tie = 0;
-            if (n_cand <= 4096) {
-                // rank by (score descending, position ascending): the order itself when no two scores are equal, and
-                // the stable order = what __final_insertion_sort leaves when run after the partition rounds below
-                auto rank_sort = [&]() {
-                    int any_tie = 0;
-                    for (int t = tid; t < n_cand; t += blockDim.x) {
-                        const float s = cand0[t].s;
-                        int rank = 0;
-                        for (int u = 0; u < n_cand; ++u) {
-                            const float su = cand0[u].s;
-                            rank += (su > s) | (su == s && u < t);
-                            any_tie |= (su == s && u != t);
-                        }
-                        cand1[rank] = cand0[t];
-                    }
-                    return __syncthreads_or(any_tie);
-                };
-                tie = rank_sort();
-                sorted = cand1;
-                if (tie && p.cand_unordered) {
-                    // std::sort's input is the candidate list in a-major / b-minor order (src/paf.cpp:93-131): put the
-                    // unordered list into that order first (rank by pair index, which is unique), back into cand0
-                    for (int t = tid; t < n_cand; t += blockDim.x) {
-                        const Cand ct = cand0[t];
-                        const unsigned key = (unsigned)(ct.i1 - ofs_a) * nb_u + (unsigned)(ct.i2 - ofs_b);
-                        int rank = 0;
-                        for (int u = 0; u < n_cand; ++u) rank += ((unsigned)(cand0[u].i1 - ofs_a) * nb_u + (unsigned)(cand0[u].i2 - ofs_b)) < key;
-                        cand1[rank] = ct;
-                    }
-                    __syncthreads();
-                    for (int t = tid; t < n_cand; t += blockDim.x) cand0[t] = cand1[t];
-                    __syncthreads();
-                }
-                if (tie && p.cand_in_smem && n_cand <= 0xffff) {
-                    // tied scores: std::sort's element movement decides.  cand1 serves as scratch in between.
-                    const Span<unsigned short> pos_a = SPAN(unsigned short, reinterpret_cast<unsigned short *>(cand1.p), n_cand);
-                    const Span<unsigned short> pos_b = SPAN(unsigned short, reinterpret_cast<unsigned short *>(cand1.p) + n_cand, n_cand);
-                    std_sort_partition_rounds(cand0, n_cand, pos_a, pos_b, SPAN(int, reinterpret_cast<int *>(smem_raw + p.off_surv), p.surv_cap));
-                    rank_sort();
-                    tie = 0;
-                }
-            } else
-                tie = 1;
-            if (tie) {
-                sorted = cand0;
-                if (tid == 0) std_sort_desc(cand0.p, n_cand);
-                __syncthreads();
-            }
-        }
+        const Span<Cand> sorted = sort_candidates_desc(cand0, cand1, n_cand, p.cand_unordered != 0, ofs_a, ofs_b, nb_u, p.cand_in_smem != 0,
+                                                       SPAN(int, reinterpret_cast<int *>(smem_raw + p.off_surv), p.surv_cap));
 
         stamp(p, frame, pair_id, 3);
         // ---- greedy matching in sorted order (src/paf.cpp:154-173): a candidate is accepted unless an accepted one
@@ -2857,6 +2883,17 @@ cudaError_t launch_ingest(const float *src0, float *dst0, size_t n0, const float
 
 // First bounds violation recorded by a -DOPP_DEBUG_BOUNDS build on the current device: {source line of the Span, index,
 // size, number of violations}; cudaErrorNotSupported in a release build.
+cudaError_t launch_debug_sort(void *cands, int n, int mode, int threads, cudaStream_t st)
+{
+    if (n < 0 || (mode == 0 && n > 4096) || threads < 32 || threads > OPP_THREADS || threads % 32) return cudaErrorInvalidValue;
+    const size_t smem = mode == 0 ? 2 * (size_t)n * sizeof(Cand) + 4 * ((size_t)n / 17 + 2) * sizeof(int) + 16 : 0;
+    int dyn_limit = 0;
+    BIG_SMEM_LIMIT(k_debug_sort, dyn_limit);
+    if (smem > (size_t)dyn_limit) return cudaErrorInvalidValue;
+    k_debug_sort<<<1, threads, smem, st>>>(reinterpret_cast<Cand *>(cands), n, mode);
+    return cudaGetLastError();
+}
+
 cudaError_t opp_kernels_bounds_report(int out[4], bool reset)
 {
 #ifdef OPP_DEBUG_BOUNDS

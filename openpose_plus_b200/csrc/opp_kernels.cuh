@@ -119,3 +119,4 @@ cudaError_t launch_ingest(const float *src0, float *dst0, size_t n0, const float
                           cudaStream_t st);
 cudaError_t opp_kernels_init(int max_smem_optin);
 cudaError_t opp_kernels_bounds_report(int out[4], bool reset);
+cudaError_t launch_debug_sort(void *cands, int n, int mode, int threads, cudaStream_t st); // cands: n x {int32 i1, int32 i2, float score}

@@ -81,6 +81,48 @@ def test_non_integer_scales_from_feature_maps_and_from_the_materialised_map(mods
             eng.close()
 
 
+def test_std_sort_emulation_on_the_device(mods):
+    """The limb kernel's two forms of std::sort(greater on score) - the parallel one (partition rounds by warps + stable rank
+    sort) and the sequential emulation - run directly on candidate lists through opp_debug_sort, against the oracle's
+    restatement of libstdc++'s introsort (pinned to the real std::sort on the CPU): heavy ties, few distinct values, sorted /
+    reversed / organ-pipe inputs, and Musser's median-of-3 adversary, which drives ranges into the depth limit (heap sort)."""
+    import ctypes as C
+    Engine, Oracle, H = mods
+    from openpose_plus_b200 import _capi as capi
+    from oracle.oracle import CAND_DT
+    eng = Engine(46, 54, max_batch=1)
+
+    def killer(n):
+        k, a = n // 2, [0] * n
+        for i in range(1, k + 1):
+            if i % 2:
+                a[i - 1], a[i] = i, k + i
+            a[k + i - 1] = 2 * i
+        return np.array(a, np.float32)
+
+    def check(scores, threads):
+        n = len(scores)
+        want = np.zeros(n, CAND_DT)
+        want["idx1"], want["score"] = np.arange(n), scores
+        want = Oracle.std_sort_desc(want)["idx1"]
+        for mode in (0, 1):
+            c = np.zeros(n, capi.CONN_DT)
+            c["cid1"], c["score"] = np.arange(n), scores
+            eng._check(eng.L.opp_debug_sort(eng.h, c.ctypes.data_as(C.c_void_p), n, mode, threads))
+            assert np.array_equal(c["cid1"], want), (n, mode, threads)
+
+    rng = np.random.default_rng(17)
+    for n in (0, 1, 2, 16, 17, 18, 33, 64, 100, 257, 1000, 1024, 4096):
+        for nd in (max(1, n), max(1, n // 3), 5, 2, 1):
+            check((rng.integers(0, nd, n) / 7).astype(np.float32), 192)
+    for n in (300, 1024, 2048):
+        for arr in (np.arange(n), np.arange(n)[::-1], np.concatenate([np.arange(n // 2), np.arange(n // 2)[::-1]]), np.repeat(np.arange(n // 8), 8),
+                    killer(n), -killer(n), np.floor(killer(n) / 3)):
+            check(np.asarray(arr, np.float32), 256 if n == 1024 else 192)
+    check((rng.integers(0, 40, 777) / 7).astype(np.float32), 32)   # a single warp takes every range in turn
+    eng.close()
+
+
 def test_dense_noise_frame(mods):
     """SURVEY 8(d)'s capacity-sizing frame: uniform-random maps (7 847 peaks, ~195 k candidate pairs and ~1 700 accepted
     candidates per limb, four limbs with tied scores, 1 300 partial humans, 99 merges).  Far beyond the staging areas of the
