@@ -2230,6 +2230,9 @@ __device__ void assemble_frame(const K3Params &p, int frame, unsigned char *smem
 
 // __grid_constant__: the parameter block is read through references (assemble_frame, the stamps); without the qualifier
 // taking its address makes every CTA copy it to local memory first
+// UNORDERED = p.cand_unordered as a compile-time constant: the default capacities never reach the ordered-compaction
+// form of the scoring loop, and the kernel's code is fetched cold (see score_pair) - what is not there is not fetched.
+template <bool UNORDERED>
 __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ K3Params p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -2368,7 +2371,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
             if (ib >= nb_u) ib -= nb_u, ++ia;
         };
         int overflow = 0, n_surv_total = 0;
-        if (p.cand_unordered) {
+        if (UNORDERED) {
             // Candidates are appended in whatever order the warps finish (one shared-memory atomic per warp and round,
             // no block-wide compaction); the sort below ranks them by (score, pair index), which is std::sort's
             // result whenever no two scores are equal, and restores the a-major / b-minor input order first when some are.
@@ -2509,7 +2512,7 @@ __global__ void __launch_bounds__(OPP_THREADS) k3_limbs(const __grid_constant__ 
 
         // ---- sort by score, descending, in std::sort's order.  With no equal scores the sorted order is
         // unique and a parallel rank sort gives it; with ties only the sequential emulation does.
-        const Span<Cand> sorted = sort_candidates_desc(cand0, cand1, n_cand, p.cand_unordered != 0, ofs_a, ofs_b, nb_u, p.cand_in_smem != 0,
+        const Span<Cand> sorted = sort_candidates_desc(cand0, cand1, n_cand, UNORDERED, ofs_a, ofs_b, nb_u, p.cand_in_smem != 0,
                                                        SPAN(int, reinterpret_cast<int *>(smem_raw + p.off_surv), p.surv_cap));
 
         stamp(p, frame, pair_id, 3);
@@ -2767,7 +2770,8 @@ cudaError_t launch_k2_generic_rep(const K2Params &p, int n_frames, cudaStream_t 
 cudaError_t launch_k3(const K3Params &p, int n_frames, size_t smem, cudaStream_t st, bool pdl)
 {
     int dyn_limit = 0;
-    BIG_SMEM_LIMIT(k3_limbs, dyn_limit);
+    if (p.cand_unordered) BIG_SMEM_LIMIT(k3_limbs<true>, dyn_limit);
+    else BIG_SMEM_LIMIT(k3_limbs<false>, dyn_limit);
     if (smem > (size_t)dyn_limit) return cudaErrorInvalidValue;
     dim3 grid(OPP_N_PAIRS, n_frames);
     // Threads per limb CTA (OPP_K3_THREADS = 128 .. 256, multiple of 32, overrides).  Most of the kernel is latency bound and
@@ -2779,7 +2783,7 @@ cudaError_t launch_k3(const K3Params &p, int n_frames, size_t smem, cudaStream_t
         const int t = e ? atoi(e) : K3_THREADS_DEFAULT;
         return (t >= 128 && t <= OPP_THREADS && t % 32 == 0) ? t : K3_THREADS_DEFAULT;
     }();
-    return launch_ex(k3_limbs, grid, dim3(threads), smem, st, pdl, p);
+    return p.cand_unordered ? launch_ex(k3_limbs<true>, grid, dim3(threads), smem, st, pdl, p) : launch_ex(k3_limbs<false>, grid, dim3(threads), smem, st, pdl, p);
 }
 
 static bool k1_fast_ok(const K1Params &p)
