@@ -100,6 +100,8 @@ struct opp_handle_s {
     bool paf_early = true; // latency path: the limb kernel fetches its PAF tiles from pinned memory itself (OPP_NO_PAF_EARLY=1 disables)
     bool done_flag = true; // completion word in pinned memory on the latency path (OPP_NO_DONE_FLAG=1 disables)
     int tag_seq = 0;
+    bool k2_store_low = true;     // full batches: fused peaks + resize kernel on the low-priority side stream, limb kernel on the high-priority one
+    bool k2_skel_low = true;      // the same for the skeleton-only peak kernel
     bool generic_via_map = false; // non-integer scales: materialise the heat map first and let the generic kernel read it
     bool generic_rep = true; // integer scales outside the fast kernel's range: replication-aware generic kernel (OPP_NO_GENERIC_REP=1: via the materialised map)
     bool stage_pageable = true; // latency path for pageable inputs through pinned staging (OPP_NO_STAGE_PAGEABLE=1: cudaMemcpyAsync from pageable memory)
@@ -621,6 +623,9 @@ int opp_create(const opp_config_t *cfg, opp_handle_t *out)
         h->pdl = getenv("OPP_NO_PDL") == nullptr;
         h->stage_pageable = getenv("OPP_NO_STAGE_PAGEABLE") == nullptr;
         h->generic_rep = getenv("OPP_NO_GENERIC_REP") == nullptr;
+        if (const char *e = getenv("OPP_K2_LOW")) h->k2_store_low = h->k2_skel_low = atoi(e) != 0;
+        if (const char *e = getenv("OPP_K2_STORE_LOW")) h->k2_store_low = atoi(e) != 0;
+        if (const char *e = getenv("OPP_K2_SKEL_LOW")) h->k2_skel_low = atoi(e) != 0;
         h->generic_via_map = getenv("OPP_GENERIC_VIA_MAP") != nullptr && atoi(getenv("OPP_GENERIC_VIA_MAP")) != 0;
         h->done_flag = getenv("OPP_NO_DONE_FLAG") == nullptr;
         h->paf_early = getenv("OPP_NO_PAF_EARLY") == nullptr;
@@ -822,7 +827,19 @@ static int enqueue(opp_handle_s *h, Slot &s, const opp_batch_t &b)
     // while their predecessor still runs; each waits (griddepcontrol.wait) before touching its results.
     const bool few = n <= h->ingest_max && !h->trace && !forked;
     const bool pdl = h->pdl && few;
-    if (h->fast_k2) {
+    if (h->fast_k2 && !few && !forked && (fuse_up ? h->k2_store_low : h->k2_skel_low)) {
+        // Full batches: the peak kernel (which wants every SM for a long time) runs on the slot's LOW-priority stream, the
+        // limb kernel (little work, latency bound) stays on the high-priority one - the limb kernels of the batches ahead
+        // get the CTA slots the peak kernel's CTAs keep freeing instead of queueing behind them.  Materialised 368x432:
+        // 163 k -> 175 k frames/s (the three slots' kernels then overlap tail to head: 0.98 of the copy peak over whole
+        // batches, above the 0.956 of one fused kernel timed alone); crowded 152 k -> 161 k; every block active, skeleton-only:
+        // 391 k -> 432 k.  OPP_K2_LOW=0 keeps both kernels on one stream.
+        CU(cudaEventRecord(s.ev_fork, st));
+        CU(cudaStreamWaitEvent(s.side, s.ev_fork, 0));
+        CU(launch_k2_fast(k2, n, s.side, false));
+        CU(cudaEventRecord(s.ev_join, s.side));
+        CU(cudaStreamWaitEvent(st, s.ev_join, 0));
+    } else if (h->fast_k2) {
         CU(launch_k2_fast(k2, n, st, pdl && ingest));
     } else {
         CU(generic_rep ? launch_k2_generic_rep(k2, n, st) : launch_k2_generic(k2, n, st));
